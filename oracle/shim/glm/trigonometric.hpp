@@ -1,0 +1,3 @@
+// oracle shim forwarder (test infrastructure) — see glm_subset.hpp
+#pragma once
+#include <glm/glm_subset.hpp>
