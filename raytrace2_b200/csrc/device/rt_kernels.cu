@@ -1,0 +1,789 @@
+// Wavefront path-tracing kernels for sm_100a and their launcher.
+//
+// Replaces RayTracer::Update / RayColor (src/cpu_raytrace/RayTracer.cpp:20-70) with a batch-synchronous wavefront:
+//
+//   k_generate            Camera::GetRay for F frames x W*H pixels            (Camera.hpp:50-67)
+//   per bounce b < max_depth:
+//     k_extend            closest hit (BVH + instances + media), hit record, push ray index into its material bin
+//     k_shade_terminal    miss -> T*background, diffuse light -> T*emit        (RayTracer.cpp:25-34,44)
+//     k_shade_scatter<m>  one launch per material bin present in the scene: new ray + throughput, written to the
+//                         next queue at a position derived from the bin counters (no atomics, queue sorted by bin)
+//   k_accumulate          accum[pixel] += radiance[f][pixel] in frame order    (RayTracer.cpp:64)
+//   k_resolve             mean, RGBA8 preview                                  (RayTracer.cpp:16-18,65-66,105-112)
+//
+// Queue sizes live in device memory (counters[bounce][8]); kernels are launched with a persistent grid and loop
+// grid-stride over the count they read there, so no host synchronisation happens inside a batch.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_render.hpp"
+#include "rt_shade.cuh"
+
+namespace rt2dev {
+
+constexpr int kBlock = 256;
+constexpr int kNumBins = 6;  // 0 terminal (miss / light), 1 lambertian, 2 texture, 3 metal, 4 dielectric, 5 isotropic
+constexpr int kCounterStride = 8;
+
+struct FrameParams {
+  rt2_camera cam;
+  uint32_t width, height, pixels;
+  uint32_t sqrt_spp;
+  float recip_sqrt_spp;
+  uint32_t frame_base;    // global index of the batch's first frame
+  uint32_t frame_stride;  // global frame of local frame lf = frame_base + lf * frame_stride
+  uint32_t seed_lo, seed_hi;
+};
+
+__device__ __forceinline__ RngKey key_of_slot(const FrameParams& fp, uint32_t slot) {
+  RngKey k;
+  k.pixel = slot % fp.pixels;
+  k.frame = fp.frame_base + (slot / fp.pixels) * fp.frame_stride;
+  k.seed_lo = fp.seed_lo;
+  k.seed_hi = fp.seed_hi;
+  return k;
+}
+
+// Camera::GetRay (Camera.hpp:50-67) + the stratum selection of RayTracer::Update (RayTracer.cpp:57-60)
+__global__ void __launch_bounds__(kBlock) k_generate(const FrameParams fp, uint32_t n_slots, float4* __restrict__ ray_o,
+                                                     float4* __restrict__ ray_d, float4* __restrict__ state,
+                                                     uint32_t* __restrict__ counters) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += stride) {
+    const RngKey key = key_of_slot(fp, slot);
+    const uint32_t x = key.pixel % fp.width, y = key.pixel / fp.width;
+    const uint32_t s_i = key.frame % fp.sqrt_spp, s_j = (key.frame / fp.sqrt_spp) % fp.sqrt_spp;
+    const uint4 r = rng_draw(key, 0, kStreamCamera);
+    const float offx = (static_cast<float>(s_i) + u01(r.x)) * fp.recip_sqrt_spp - 0.5f;
+    const float offy = (static_cast<float>(s_j) + u01(r.y)) * fp.recip_sqrt_spp - 0.5f;
+    const float fx = static_cast<float>(x) + offx, fy = static_cast<float>(y) + offy;
+    F3 pc = {fp.cam.pixel00[0] + fx * fp.cam.pixel_delta_u[0] + fy * fp.cam.pixel_delta_v[0],
+             fp.cam.pixel00[1] + fx * fp.cam.pixel_delta_u[1] + fy * fp.cam.pixel_delta_v[1],
+             fp.cam.pixel00[2] + fx * fp.cam.pixel_delta_u[2] + fy * fp.cam.pixel_delta_v[2]};
+    F3 c = {fp.cam.center[0], fp.cam.center[1], fp.cam.center[2]};
+    if (fp.cam.defocus_angle > 0.0f) {
+      // math::RandInUnitDisk (Math.hpp:34-41) sampled directly: uniform over the unit disk
+      const uint4 l = rng_draw(key, 0, kStreamLens);
+      float rr = sqrtf(u01(l.x)), s, co;
+      sincospif(2.0f * u01(l.y), &s, &co);
+      const float p0 = rr * co, p1 = rr * s;
+      c = {c.x + p0 * fp.cam.defocus_disk_u[0] + p1 * fp.cam.defocus_disk_v[0],
+           c.y + p0 * fp.cam.defocus_disk_u[1] + p1 * fp.cam.defocus_disk_v[1],
+           c.z + p0 * fp.cam.defocus_disk_u[2] + p1 * fp.cam.defocus_disk_v[2]};
+    }
+    const F3 dir = normalize3(F3{pc.x - c.x, pc.y - c.y, pc.z - c.z});
+    ray_o[slot] = make_float4(c.x, c.y, c.z, u01(r.z));  // .w = ray time
+    ray_d[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+    state[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(slot));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = n_slots;
+}
+
+__device__ __forceinline__ int bin_of_material(const DeviceScene& S, int32_t material) {
+  if (material < 0) return 0;
+  const uint32_t type = __float_as_uint(__ldg(S.materials + 2 * material).x);
+  switch (type) {
+    case RT2_MAT_LAMBERTIAN: return 1;
+    case RT2_MAT_TEXTURE: return 2;
+    case RT2_MAT_METAL: return 3;
+    case RT2_MAT_DIELECTRIC: return 4;
+    case RT2_MAT_ISOTROPIC: return 5;
+    default: return 0;  // diffuse light (terminal)
+  }
+}
+
+// Warp-aggregated append of `value` to queue `bin` (one atomic per distinct bin per warp).
+__device__ __forceinline__ void bin_push(uint32_t* __restrict__ counters, uint32_t* __restrict__ queues, uint32_t queue_stride,
+                                         int bin, uint32_t value) {
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, bin);
+  const int leader = __ffs(peers) - 1;
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t base = 0;
+  if (static_cast<int>(lane) == leader) base = atomicAdd(&counters[1 + bin], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+  queues[static_cast<size_t>(bin) * queue_stride + pos] = value;
+}
+
+// one buffer, kNumBins regions of `stride` entries
+struct BinQueues {
+  uint32_t* base;
+  uint32_t stride;
+  __host__ __device__ uint32_t* q(int bin) const { return base + static_cast<size_t>(bin) * stride; }
+};
+
+// Closest hit for every queued ray of this bounce; hit record out; ray index appended to its material bin.
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_extend(const DeviceScene S, const FrameParams fp, uint32_t bounce,
+                                                   uint32_t* __restrict__ counters, const float4* __restrict__ ray_o,
+                                                   const float4* __restrict__ ray_d, const float4* __restrict__ state,
+                                                   float4* __restrict__ hit0, float4* __restrict__ hit1, BinQueues bins) {
+  const uint32_t n = counters[0];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float4 o = ray_o[i], d = ray_d[i];
+    const uint32_t slot = __float_as_uint(state[i].w);
+    const RngKey key = key_of_slot(fp, slot);
+    HitOut h;
+    // scene.hittable_list.Hit(scene, r, Interval{0.001, kInfinity}, rec)  (RayTracer.cpp:25)
+    closest_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, kFltMax, key, bounce, false, h);
+    hit0[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t);
+    const uint32_t mbits = (h.material < 0) ? 0xFFFFFFFFu : (static_cast<uint32_t>(h.material) | (h.front_face ? 0x80000000u : 0u));
+    hit1[i] = make_float4(h.n.x, h.n.y, h.n.z, __uint_as_float(mbits));
+    bin_push(counters, bins.base, bins.stride, bin_of_material(S, h.material), i);
+  }
+}
+
+// Paths that end here: miss -> background, emitter -> Emit (both faces).  radiance[slot] = throughput * colour.
+__global__ void __launch_bounds__(kBlock) k_shade_terminal(const DeviceScene S, uint32_t* __restrict__ counters,
+                                                           uint32_t* __restrict__ next_counters, const uint32_t* __restrict__ queue,
+                                                           const float4* __restrict__ state, const float4* __restrict__ hit0,
+                                                           const float4* __restrict__ hit1, float4* __restrict__ radiance) {
+  const uint32_t n = counters[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && next_counters != nullptr) {
+    // every ray in a scattering bin produces exactly one ray for the next bounce
+    next_counters[0] = counters[2] + counters[3] + counters[4] + counters[5] + counters[6];
+  }
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const uint32_t i = queue[j];
+    const float4 st = state[i];
+    const float4 h1 = hit1[i];
+    const uint32_t mbits = __float_as_uint(h1.w);
+    F3 c;
+    if (mbits == 0xFFFFFFFFu) {
+      c = {S.background[0], S.background[1], S.background[2]};
+    } else {
+      const float4 h0 = hit0[i];
+      const float4 m0 = __ldg(S.materials + 2 * (mbits & 0x7FFFFFFFu));
+      c = texture_value(S, __float_as_uint(m0.y), make_f3(h0));  // DiffuseLight::Emit (Material.cpp:71-74)
+    }
+    radiance[__float_as_uint(st.w)] = make_float4(st.x * c.x, st.y * c.y, st.z * c.z, 0.0f);
+  }
+}
+
+template <int kType, int kBin>
+__global__ void __launch_bounds__(kBlock) k_shade_scatter(const DeviceScene S, const FrameParams fp, uint32_t bounce,
+                                                          const uint32_t* __restrict__ counters, const uint32_t* __restrict__ queue,
+                                                          const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                          const float4* __restrict__ state, const float4* __restrict__ hit0,
+                                                          const float4* __restrict__ hit1, float4* __restrict__ out_o,
+                                                          float4* __restrict__ out_d, float4* __restrict__ out_state) {
+  const uint32_t n = counters[1 + kBin];
+  uint32_t base = 0;
+#pragma unroll
+  for (int b = 1; b < kBin; b++) base += counters[1 + b];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const uint32_t i = queue[j];
+    const float4 st = state[i];
+    const float4 h0 = hit0[i], h1 = hit1[i];
+    const float4 d = ray_d[i];
+    const float time = ray_o[i].w;
+    const uint32_t mbits = __float_as_uint(h1.w);
+    const uint32_t mat = mbits & 0x7FFFFFFFu;
+    const float4 m0 = __ldg(S.materials + 2 * mat), m1 = __ldg(S.materials + 2 * mat + 1);
+    const RngKey key = key_of_slot(fp, __float_as_uint(st.w));
+    const uint4 r = rng_draw(key, bounce, kStreamScatter);
+    F3 dir;
+    const F3 att = scatter<kType>(S, m0, m1, make_f3(d), make_f3(h0), make_f3(h1), (mbits >> 31) != 0u, r, dir);
+    const uint32_t dst = base + j;
+    out_o[dst] = make_float4(h0.x, h0.y, h0.z, time);
+    out_d[dst] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+    out_state[dst] = make_float4(st.x * att.x, st.y * att.y, st.z * att.z, st.w);
+  }
+}
+
+// accumulation_data_[idx] += ray_color, one frame after the other (RayTracer.cpp:64) — fixed order, no atomics.
+__global__ void __launch_bounds__(kBlock) k_accumulate(uint32_t pixels, uint32_t n_frames, const float4* __restrict__ radiance,
+                                                       float4* __restrict__ accum, float4* __restrict__ accum_sq) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += stride) {
+    float4 a = accum[p];
+    float4 s = accum_sq ? accum_sq[p] : make_float4(0, 0, 0, 0);
+    for (uint32_t f = 0; f < n_frames; f++) {
+      const float4 v = radiance[static_cast<size_t>(f) * pixels + p];
+      a.x += v.x;
+      a.y += v.y;
+      a.z += v.z;
+      s.x += v.x * v.x;
+      s.y += v.y * v.y;
+      s.z += v.z * v.z;
+    }
+    accum[p] = a;
+    if (accum_sq) accum_sq[p] = s;
+  }
+}
+
+// NonConvertedPixels (RayTracer.cpp:105-112) and the RGBA8 preview (RayTracer.cpp:16-18,65-66)
+__global__ void __launch_bounds__(kBlock) k_resolve(uint32_t pixels, float frames, const float4* __restrict__ accum,
+                                                    float* __restrict__ mean_rgb, uchar4* __restrict__ rgba8) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += stride) {
+    const float4 a = accum[p];
+    const float mx = a.x / frames, my = a.y / frames, mz = a.z / frames;
+    if (mean_rgb) {
+      mean_rgb[3 * p + 0] = mx;
+      mean_rgb[3 * p + 1] = my;
+      mean_rgb[3 * p + 2] = mz;
+    }
+    if (rgba8) {
+      // ToColor(glm::clamp(mean, 0, 1)): floor(c * 255.999) in double, then converted to uint8
+      const double cx = floor(static_cast<double>(fminf(fmaxf(mx, 0.0f), 1.0f)) * 255.999);
+      const double cy = floor(static_cast<double>(fminf(fmaxf(my, 0.0f), 1.0f)) * 255.999);
+      const double cz = floor(static_cast<double>(fminf(fmaxf(mz, 0.0f), 1.0f)) * 255.999);
+      rgba8[p] = make_uchar4(static_cast<unsigned char>(cx), static_cast<unsigned char>(cy), static_cast<unsigned char>(cz), 255);
+    }
+  }
+}
+
+// rays traced in this batch = sum over bounces of the queue sizes
+__global__ void k_batch_stats(const uint32_t* __restrict__ counters, uint32_t max_depth, unsigned long long* __restrict__ totals) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long rays = 0;
+    for (uint32_t b = 0; b < max_depth; b++) rays += counters[b * kCounterStride];
+    totals[0] += rays;
+    totals[1] += counters[0];
+  }
+}
+
+// Fixed-ray parity hook (rt2_intersect): one thread per ray, full record out.
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_intersect(const DeviceScene S, const float4* __restrict__ rays, uint32_t n, float tmin,
+                                                      float tmax, int skip_media, uint32_t seed_lo, uint32_t seed_hi,
+                                                      rt2_hit* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 o = rays[2 * i], d = rays[2 * i + 1];
+  RngKey key{i, 0u, seed_lo, seed_hi};
+  HitOut h;
+  closest_hit<M>(S, make_f3(o), make_f3(d), o.w, tmin, tmax, key, 0, skip_media != 0, h);
+  rt2_hit r;
+  r.point[0] = h.p.x, r.point[1] = h.p.y, r.point[2] = h.p.z;
+  r.t = h.t;
+  r.normal[0] = h.n.x, r.normal[1] = h.n.y, r.normal[2] = h.n.z;
+  r.material = h.material;
+  r.prim = (h.material < 0) ? RT2_PRIM_NONE : h.prim;
+  r.instance = (h.material < 0) ? -1 : h.instance;
+  r.front_face = h.front_face ? 1u : 0u;
+  r.pad = 0;
+  out[i] = r;
+}
+
+}  // namespace rt2dev
+
+// ===================================================================================================================
+// Host-side launcher
+// ===================================================================================================================
+namespace rt2 {
+
+using namespace rt2dev;
+
+#define RT2_CUDA(call)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      err_ = std::string(#call) + " failed: " + cudaGetErrorString(e__);                                \
+      return RT2_ERR_CUDA;                                                                               \
+    }                                                                                                    \
+  } while (0)
+
+struct Renderer::Impl {
+  DeviceScene ds{};
+  // scene buffers
+  void* d_spheres{nullptr};
+  void* d_quads{nullptr};
+  void* d_xforms{nullptr};
+  void* d_instances{nullptr};
+  void* d_media{nullptr};
+  void* d_materials{nullptr};
+  void* d_textures{nullptr};
+  void* d_perlin{nullptr};
+  void* d_prim_refs{nullptr};
+  void* d_nodes{nullptr};
+  size_t cap_spheres{0}, cap_quads{0}, cap_xforms{0}, cap_instances{0}, cap_media{0}, cap_materials{0}, cap_textures{0},
+      cap_perlin{0}, cap_prim_refs{0}, cap_nodes{0};
+  // wavefront state
+  float4* ray_o[2]{nullptr, nullptr};
+  float4* ray_d[2]{nullptr, nullptr};
+  float4* state[2]{nullptr, nullptr};
+  float4* hit0{nullptr};
+  float4* hit1{nullptr};
+  BinQueues bins{};
+  uint32_t* counters{nullptr};
+  float4* radiance{nullptr};
+  float4* accum{nullptr};
+  float4* accum_sq{nullptr};
+  float* mean_rgb{nullptr};
+  uchar4* rgba8{nullptr};
+  unsigned long long* totals{nullptr};
+  cudaStream_t stream{nullptr};
+  cudaEvent_t ev_start{nullptr}, ev_stop{nullptr};
+  int grid_extend{0}, grid_stream{0};
+  bool bin_present[kNumBins]{};
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_kind;
+};
+
+Renderer::Renderer() : impl_(new Impl) {}
+
+Renderer::~Renderer() {
+  if (!impl_) return;
+  cudaSetDevice(cfg_.device);
+  FreeState();
+  Impl& m = *impl_;
+  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (m.totals) cudaFree(m.totals);
+  if (m.ev_start) cudaEventDestroy(m.ev_start);
+  if (m.ev_stop) cudaEventDestroy(m.ev_stop);
+  for (cudaEvent_t e : m.prof_events) cudaEventDestroy(e);
+  if (m.stream) cudaStreamDestroy(m.stream);
+  delete impl_;
+}
+
+void Renderer::FreeState() {
+  Impl& m = *impl_;
+  void* bufs[] = {m.ray_o[0], m.ray_o[1], m.ray_d[0], m.ray_d[1], m.state[0], m.state[1], m.hit0, m.hit1, m.counters,
+                  m.radiance, m.accum, m.accum_sq, m.mean_rgb, m.rgba8};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (m.bins.base) cudaFree(m.bins.base);
+  m.bins.base = nullptr;
+  m.ray_o[0] = m.ray_o[1] = m.ray_d[0] = m.ray_d[1] = m.state[0] = m.state[1] = m.hit0 = m.hit1 = nullptr;
+  m.counters = nullptr;
+  m.radiance = m.accum = m.accum_sq = nullptr;
+  m.mean_rgb = nullptr;
+  m.rgba8 = nullptr;
+}
+
+int Renderer::Init(const HostScene& scene, const rt2_config& cfg) {
+  cfg_ = cfg;
+  Impl& m = *impl_;
+  int n_dev = 0;
+  RT2_CUDA(cudaGetDeviceCount(&n_dev));
+  if (cfg.device < 0 || cfg.device >= n_dev) {
+    err_ = "CUDA device " + std::to_string(cfg.device) + " not available (" + std::to_string(n_dev) + " devices)";
+    return RT2_ERR_CUDA;
+  }
+  RT2_CUDA(cudaSetDevice(cfg.device));
+  cudaDeviceProp prop;
+  RT2_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+  sm_count_ = prop.multiProcessorCount;
+  RT2_CUDA(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
+  RT2_CUDA(cudaEventCreate(&m.ev_start));
+  RT2_CUDA(cudaEventCreate(&m.ev_stop));
+  RT2_CUDA(cudaMalloc(&m.totals, 4 * sizeof(unsigned long long)));
+  RT2_CUDA(cudaMemset(m.totals, 0, 4 * sizeof(unsigned long long)));
+  if (cfg_.max_depth < 1) cfg_.max_depth = 1;
+  if (cfg_.samples_per_pixel < 1) cfg_.samples_per_pixel = 1;
+  if (cfg_.frame_stride < 1) cfg_.frame_stride = 1;
+  // persistent grids: resident blocks per SM x SM count
+  int occ = 0;
+  if (cfg_.flags & RT2_FLAG_FAST_MATH) {
+    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<FastMath>, kBlock, 0));
+  } else {
+    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<ExactMath>, kBlock, 0));
+  }
+  if (occ < 1) occ = 1;
+  m.grid_extend = sm_count_ * occ;
+  m.grid_stream = sm_count_ * 8;
+  int rc = UploadScene(scene);
+  if (rc != RT2_OK) return rc;
+  int w = cfg.width > 0 ? cfg.width : scene.width;
+  int h = cfg.height > 0 ? cfg.height : scene.height;
+  return Resize(w, h);
+}
+
+template <class T>
+static int UploadBuf(void** dptr, size_t* cap, const std::vector<T>& v, cudaStream_t stream, std::string* err) {
+  size_t bytes = v.size() * sizeof(T);
+  if (bytes > *cap || *dptr == nullptr) {
+    if (*dptr) cudaFree(*dptr);
+    size_t alloc = bytes > 0 ? bytes : 16;
+    cudaError_t e = cudaMalloc(dptr, alloc);
+    if (e != cudaSuccess) {
+      *err = std::string("cudaMalloc(scene buffer) failed: ") + cudaGetErrorString(e);
+      return RT2_ERR_CUDA;
+    }
+    *cap = alloc;
+  }
+  if (bytes) {
+    cudaError_t e = cudaMemcpyAsync(*dptr, v.data(), bytes, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) {
+      *err = std::string("cudaMemcpyAsync(scene buffer) failed: ") + cudaGetErrorString(e);
+      return RT2_ERR_CUDA;
+    }
+  }
+  return RT2_OK;
+}
+
+int Renderer::UploadScene(const HostScene& scene) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  int rc;
+#define UP(field, vec, cap)                                                   \
+  rc = UploadBuf(&m.field, &m.cap, scene.vec, m.stream, &err_);               \
+  if (rc != RT2_OK) return rc;
+  UP(d_spheres, spheres, cap_spheres)
+  UP(d_quads, quads, cap_quads)
+  UP(d_xforms, xforms, cap_xforms)
+  UP(d_instances, instances, cap_instances)
+  UP(d_media, media, cap_media)
+  UP(d_materials, materials, cap_materials)
+  UP(d_textures, textures, cap_textures)
+  UP(d_perlin, perlin, cap_perlin)
+  UP(d_prim_refs, prim_refs, cap_prim_refs)
+  UP(d_nodes, nodes, cap_nodes)
+#undef UP
+  scene_bytes_ = scene.spheres.size() * sizeof(rt2_sphere) + scene.quads.size() * sizeof(rt2_quad) +
+                 scene.xforms.size() * sizeof(rt2_xform) + scene.instances.size() * sizeof(rt2_instance) +
+                 scene.media.size() * sizeof(rt2_medium) + scene.materials.size() * sizeof(rt2_material) +
+                 scene.textures.size() * sizeof(rt2_texture) + scene.perlin.size() * sizeof(rt2_perlin) +
+                 scene.prim_refs.size() * sizeof(uint32_t) + scene.nodes.size() * sizeof(rt2_bvh_node);
+  DeviceScene& d = m.ds;
+  d.spheres = static_cast<const float4*>(m.d_spheres);
+  d.quads = static_cast<const float4*>(m.d_quads);
+  d.xforms = static_cast<const float4*>(m.d_xforms);
+  d.instances = static_cast<const uint4*>(m.d_instances);
+  d.media = static_cast<const uint4*>(m.d_media);
+  d.materials = static_cast<const float4*>(m.d_materials);
+  d.textures = static_cast<const float4*>(m.d_textures);
+  d.perlin = static_cast<const rt2_perlin*>(m.d_perlin);
+  d.prim_refs = static_cast<const uint32_t*>(m.d_prim_refs);
+  d.nodes = static_cast<const float4*>(m.d_nodes);
+  d.tlas_root = scene.tlas_root;
+  d.n_media = static_cast<uint32_t>(scene.media.size());
+  d.n_instances = static_cast<uint32_t>(scene.instances.size());
+  d.min_inv_scale = scene.min_inv_scale;
+  for (int k = 0; k < 3; k++) d.background[k] = scene.background[k];
+  // which material bins can ever be non-empty
+  for (int b = 0; b < kNumBins; b++) m.bin_present[b] = false;
+  m.bin_present[0] = true;
+  for (const rt2_material& mat : scene.materials) {
+    switch (mat.type) {
+      case RT2_MAT_LAMBERTIAN: m.bin_present[1] = true; break;
+      case RT2_MAT_TEXTURE: m.bin_present[2] = true; break;
+      case RT2_MAT_METAL: m.bin_present[3] = true; break;
+      case RT2_MAT_DIELECTRIC: m.bin_present[4] = true; break;
+      case RT2_MAT_ISOTROPIC: m.bin_present[5] = true; break;
+      default: break;
+    }
+  }
+  cam_params_ = scene.cam;
+  return RT2_OK;
+}
+
+int Renderer::Resize(int w, int h) {
+  Impl& m = *impl_;
+  if (w <= 0 || h <= 0) {
+    err_ = "invalid dims";
+    return RT2_ERR_INVALID_ARG;
+  }
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  RT2_CUDA(cudaStreamSynchronize(m.stream));
+  FreeState();
+  width_ = w;
+  height_ = h;
+  // camera for the new dims (Camera::SetDims + Update)
+  HostScene tmp;
+  tmp.cam = cam_params_;
+  tmp.width = w;
+  tmp.height = h;
+  tmp.UpdateCamera();
+  camera_ = tmp.camera_block;
+  const size_t P = static_cast<size_t>(w) * h;
+  int F = cfg_.frames_per_batch;
+  if (F <= 0) {
+    F = static_cast<int>((6u * 1024u * 1024u + P - 1) / P);  // ~6M paths in flight
+    if (F < 1) F = 1;
+    if (F > 64) F = 64;
+  }
+  frames_per_batch_ = F;
+  const size_t N = P * static_cast<size_t>(F);
+  if (N >= 0xFFFFFFF0ull) {
+    err_ = "batch too large";
+    return RT2_ERR_INVALID_ARG;
+  }
+  for (int i = 0; i < 2; i++) {
+    RT2_CUDA(cudaMalloc(&m.ray_o[i], N * sizeof(float4)));
+    RT2_CUDA(cudaMalloc(&m.ray_d[i], N * sizeof(float4)));
+    RT2_CUDA(cudaMalloc(&m.state[i], N * sizeof(float4)));
+  }
+  RT2_CUDA(cudaMalloc(&m.hit0, N * sizeof(float4)));
+  RT2_CUDA(cudaMalloc(&m.hit1, N * sizeof(float4)));
+  RT2_CUDA(cudaMalloc(&m.bins.base, N * kNumBins * sizeof(uint32_t)));
+  m.bins.stride = static_cast<uint32_t>(N);
+  RT2_CUDA(cudaMalloc(&m.counters, static_cast<size_t>(cfg_.max_depth + 1) * kCounterStride * sizeof(uint32_t)));
+  RT2_CUDA(cudaMalloc(&m.radiance, N * sizeof(float4)));
+  RT2_CUDA(cudaMalloc(&m.accum, P * sizeof(float4)));
+  if (cfg_.flags & RT2_FLAG_MOMENTS) RT2_CUDA(cudaMalloc(&m.accum_sq, P * sizeof(float4)));
+  RT2_CUDA(cudaMalloc(&m.mean_rgb, P * 3 * sizeof(float)));
+  RT2_CUDA(cudaMalloc(&m.rgba8, P * sizeof(uchar4)));
+  return Reset();
+}
+
+int Renderer::Reset() {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  const size_t P = static_cast<size_t>(width_) * height_;
+  RT2_CUDA(cudaMemsetAsync(m.accum, 0, P * sizeof(float4), m.stream));
+  if (m.accum_sq) RT2_CUDA(cudaMemsetAsync(m.accum_sq, 0, P * sizeof(float4), m.stream));
+  RT2_CUDA(cudaMemsetAsync(m.totals, 0, 4 * sizeof(unsigned long long), m.stream));
+  frame_idx_ = 0;
+  gpu_ms_total_ = 0;
+  for (double& v : prof_ms_) v = 0;
+  return RT2_OK;
+}
+
+template <int kType, int kBin>
+static void LaunchScatter(const Renderer::Impl& m, const FrameParams& fp, uint32_t bounce, uint32_t* ctr, int in, int out) {
+  k_shade_scatter<kType, kBin><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, bounce, ctr, m.bins.q(kBin), m.ray_o[in], m.ray_d[in],
+                                                                       m.state[in], m.hit0, m.hit1, m.ray_o[out], m.ray_d[out],
+                                                                       m.state[out]);
+}
+
+int Renderer::RenderBatch(uint32_t n_frames) {
+  Impl& m = *impl_;
+  const uint32_t P = static_cast<uint32_t>(width_) * height_;
+  const uint32_t n_slots = P * n_frames;
+  FrameParams fp;
+  fp.cam = camera_;
+  fp.width = width_;
+  fp.height = height_;
+  fp.pixels = P;
+  // Camera::Update: sqrt_samples_per_pix_ = int(sqrt(samples_per_pixel)), recip = 1.0 / sqrt (Camera.hpp:45-47)
+  int sq = static_cast<int>(std::sqrt(static_cast<double>(cfg_.samples_per_pixel)));
+  if (sq < 1) sq = 1;
+  fp.sqrt_spp = sq;
+  fp.recip_sqrt_spp = static_cast<float>(1.0 / sq);
+  fp.frame_stride = cfg_.frame_stride;
+  fp.frame_base = static_cast<uint32_t>(cfg_.frame_offset + frame_idx_ * cfg_.frame_stride);
+  fp.seed_lo = static_cast<uint32_t>(cfg_.seed);
+  fp.seed_hi = static_cast<uint32_t>(cfg_.seed >> 32);
+  const bool exact = !(cfg_.flags & RT2_FLAG_FAST_MATH);
+  const uint32_t max_depth = static_cast<uint32_t>(cfg_.max_depth);
+
+  auto prof = [&](int kind) {
+    if (!profiling_) return;
+    cudaEvent_t e;
+    if (prof_used_ < m.prof_events.size()) {
+      e = m.prof_events[prof_used_];
+    } else {
+      cudaEventCreate(&e);
+      m.prof_events.push_back(e);
+      m.prof_kind.push_back(0);
+    }
+    m.prof_kind[prof_used_] = kind;
+    prof_used_++;
+    cudaEventRecord(e, m.stream);
+  };
+  prof_used_ = 0;
+
+  RT2_CUDA(cudaMemsetAsync(m.counters, 0, static_cast<size_t>(max_depth + 1) * kCounterStride * sizeof(uint32_t), m.stream));
+  RT2_CUDA(cudaMemsetAsync(m.radiance, 0, static_cast<size_t>(n_slots) * sizeof(float4), m.stream));
+  prof(0);
+  k_generate<<<m.grid_stream, kBlock, 0, m.stream>>>(fp, n_slots, m.ray_o[0], m.ray_d[0], m.state[0], m.counters);
+  launches_++;
+  int in = 0;
+  for (uint32_t b = 0; b < max_depth; b++) {
+    uint32_t* ctr = m.counters + static_cast<size_t>(b) * kCounterStride;
+    uint32_t* next = m.counters + static_cast<size_t>(b + 1) * kCounterStride;
+    const int out = in ^ 1;
+    prof(1);
+    if (exact) {
+      k_extend<ExactMath><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.hit0,
+                                                                  m.hit1, m.bins);
+    } else {
+      k_extend<FastMath><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.hit0,
+                                                                 m.hit1, m.bins);
+    }
+    launches_++;
+    prof(2);
+    const bool last = (b + 1 == max_depth);  // RayColor(depth <= 0) returns black: nothing to scatter into
+    k_shade_terminal<<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, last ? nullptr : next, m.bins.q(0), m.state[in], m.hit0, m.hit1,
+                                                             m.radiance);
+    launches_++;
+    if (!last) {
+      if (m.bin_present[1]) LaunchScatter<RT2_MAT_LAMBERTIAN, 1>(m, fp, b, ctr, in, out), launches_++;
+      if (m.bin_present[2]) LaunchScatter<RT2_MAT_TEXTURE, 2>(m, fp, b, ctr, in, out), launches_++;
+      if (m.bin_present[3]) LaunchScatter<RT2_MAT_METAL, 3>(m, fp, b, ctr, in, out), launches_++;
+      if (m.bin_present[4]) LaunchScatter<RT2_MAT_DIELECTRIC, 4>(m, fp, b, ctr, in, out), launches_++;
+      if (m.bin_present[5]) LaunchScatter<RT2_MAT_ISOTROPIC, 5>(m, fp, b, ctr, in, out), launches_++;
+    }
+    in = out;
+  }
+  prof(0);
+  k_accumulate<<<m.grid_stream, kBlock, 0, m.stream>>>(P, n_frames, m.radiance, m.accum, m.accum_sq);
+  k_batch_stats<<<1, 32, 0, m.stream>>>(m.counters, max_depth, m.totals);
+  launches_ += 2;
+  prof(3);
+  RT2_CUDA(cudaGetLastError());
+  if (profiling_) {
+    RT2_CUDA(cudaStreamSynchronize(m.stream));
+    for (size_t i = 0; i + 1 < prof_used_; i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, m.prof_events[i], m.prof_events[i + 1]);
+      int kind = m.prof_kind[i];
+      if (kind >= 0 && kind < 3) prof_ms_[kind] += ms;
+    }
+  }
+  return RT2_OK;
+}
+
+int Renderer::Update(uint32_t n_frames) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  RT2_CUDA(cudaEventRecord(m.ev_start, m.stream));
+  while (n_frames > 0) {
+    uint32_t f = n_frames < static_cast<uint32_t>(frames_per_batch_) ? n_frames : static_cast<uint32_t>(frames_per_batch_);
+    int rc = RenderBatch(f);
+    if (rc != RT2_OK) return rc;
+    frame_idx_ += f;
+    n_frames -= f;
+  }
+  RT2_CUDA(cudaEventRecord(m.ev_stop, m.stream));
+  timing_pending_ = true;
+  return RT2_OK;
+}
+
+int Renderer::Synchronize() {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  RT2_CUDA(cudaStreamSynchronize(m.stream));
+  if (timing_pending_) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, m.ev_start, m.ev_stop) == cudaSuccess) gpu_ms_total_ += ms;
+    timing_pending_ = false;
+  }
+  return RT2_OK;
+}
+
+int Renderer::ReadMean(float* dst) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  const uint32_t P = static_cast<uint32_t>(width_) * height_;
+  // accum / frame_idx_ — with no frames the reference divides by zero (NaN); we do the same
+  k_resolve<<<m.grid_stream, kBlock, 0, m.stream>>>(P, static_cast<float>(frame_idx_), m.accum, m.mean_rgb, nullptr);
+  launches_++;
+  RT2_CUDA(cudaMemcpyAsync(dst, m.mean_rgb, static_cast<size_t>(P) * 3 * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
+  return Synchronize();
+}
+
+int Renderer::ReadRGBA8(uint8_t* dst) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  const uint32_t P = static_cast<uint32_t>(width_) * height_;
+  k_resolve<<<m.grid_stream, kBlock, 0, m.stream>>>(P, static_cast<float>(frame_idx_), m.accum, nullptr, m.rgba8);
+  launches_++;
+  RT2_CUDA(cudaMemcpyAsync(dst, m.rgba8, static_cast<size_t>(P) * 4, cudaMemcpyDeviceToHost, m.stream));
+  return Synchronize();
+}
+
+int Renderer::ReadAccum(float* sum, float* sumsq) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  int rc = Synchronize();
+  if (rc != RT2_OK) return rc;
+  const size_t P = static_cast<size_t>(width_) * height_;
+  std::vector<float4> tmp(P);
+  auto fetch = [&](const float4* src, float* dst) -> int {
+    RT2_CUDA(cudaMemcpy(tmp.data(), src, P * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < P; i++) {
+      dst[3 * i + 0] = tmp[i].x;
+      dst[3 * i + 1] = tmp[i].y;
+      dst[3 * i + 2] = tmp[i].z;
+    }
+    return RT2_OK;
+  };
+  if (sum) {
+    rc = fetch(m.accum, sum);
+    if (rc != RT2_OK) return rc;
+  }
+  if (sumsq) {
+    if (!m.accum_sq) {
+      err_ = "renderer was created without RT2_FLAG_MOMENTS";
+      return RT2_ERR_STATE;
+    }
+    rc = fetch(m.accum_sq, sumsq);
+    if (rc != RT2_OK) return rc;
+  }
+  return RT2_OK;
+}
+
+int Renderer::AccumDevicePtr(void** ptr, size_t* n_floats) {
+  *ptr = impl_->accum;
+  *n_floats = static_cast<size_t>(width_) * height_ * 4;
+  return RT2_OK;
+}
+
+void* Renderer::Stream() { return impl_->stream; }
+
+int Renderer::Intersect(const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (n == 0) return RT2_OK;
+  if (n > 0x7FFFFFFFull) {
+    err_ = "too many rays";
+    return RT2_ERR_INVALID_ARG;
+  }
+  float4* d_rays = nullptr;
+  rt2_hit* d_out = nullptr;
+  RT2_CUDA(cudaMalloc(&d_rays, n * 2 * sizeof(float4)));
+  cudaError_t e = cudaMalloc(&d_out, n * sizeof(rt2_hit));
+  if (e != cudaSuccess) {
+    cudaFree(d_rays);
+    err_ = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+    return RT2_ERR_CUDA;
+  }
+  cudaMemcpyAsync(d_rays, rays, n * 2 * sizeof(float4), cudaMemcpyHostToDevice, m.stream);
+  const uint32_t grid = static_cast<uint32_t>((n + kBlock - 1) / kBlock);
+  if (cfg_.flags & RT2_FLAG_FAST_MATH) {
+    k_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_rays, static_cast<uint32_t>(n), tmin, tmax, skip_media,
+                                                         static_cast<uint32_t>(cfg_.seed), static_cast<uint32_t>(cfg_.seed >> 32), d_out);
+  } else {
+    k_intersect<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_rays, static_cast<uint32_t>(n), tmin, tmax, skip_media,
+                                                          static_cast<uint32_t>(cfg_.seed), static_cast<uint32_t>(cfg_.seed >> 32), d_out);
+  }
+  launches_++;
+  cudaMemcpyAsync(out, d_out, n * sizeof(rt2_hit), cudaMemcpyDeviceToHost, m.stream);
+  e = cudaStreamSynchronize(m.stream);
+  cudaFree(d_rays);
+  cudaFree(d_out);
+  if (e != cudaSuccess) {
+    err_ = std::string("k_intersect failed: ") + cudaGetErrorString(e);
+    return RT2_ERR_CUDA;
+  }
+  return RT2_OK;
+}
+
+int Renderer::GetStats(rt2_stats* out) {
+  Impl& m = *impl_;
+  int rc = Synchronize();
+  if (rc != RT2_OK) return rc;
+  unsigned long long t[4];
+  RT2_CUDA(cudaMemcpy(t, m.totals, sizeof(t), cudaMemcpyDeviceToHost));
+  out->rays = t[0];
+  out->paths = t[1];
+  out->frames = frame_idx_;
+  out->launches = launches_;
+  out->gpu_ms_total = gpu_ms_total_;
+  out->gpu_ms_other = prof_ms_[0];
+  out->gpu_ms_extend = prof_ms_[1];
+  out->gpu_ms_shade = prof_ms_[2];
+  return RT2_OK;
+}
+
+int DeviceCount() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+}  // namespace rt2

@@ -1,0 +1,64 @@
+// Host-side handle of the wavefront renderer (implementation in rt_kernels.cu).  Mirrors the state of
+// raytrace2::cpu::RayTracer (src/cpu_raytrace/RayTracer.hpp:15-42): dims, frame index, accumulation buffer.
+#pragma once
+#include <cstdint>
+#include <string>
+
+#include "../../../include/rt2.h"
+#include "../host/scene_host.hpp"
+
+namespace rt2 {
+
+class Renderer {
+ public:
+  struct Impl;
+  Renderer();
+  ~Renderer();
+  Renderer(const Renderer&) = delete;
+  Renderer& operator=(const Renderer&) = delete;
+
+  int Init(const HostScene& scene, const rt2_config& cfg);
+  int UploadScene(const HostScene& scene);
+  int Resize(int w, int h);          // RayTracer::OnResize
+  int Reset();                       // RayTracer::Reset
+  int Update(uint32_t n_frames);     // n x RayTracer::Update
+  int Synchronize();
+  int ReadMean(float* dst);          // RayTracer::NonConvertedPixels
+  int ReadRGBA8(uint8_t* dst);       // RayTracer::Pixels
+  int ReadAccum(float* sum, float* sumsq);
+  int AccumDevicePtr(void** ptr, size_t* n_floats);
+  int Intersect(const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out);
+  int GetStats(rt2_stats* out);
+  void* Stream();
+  void SetProfiling(bool on) { profiling_ = on; }
+  void SetFrameIdx(uint64_t f) { frame_idx_ = f; }
+  uint64_t FrameIdx() const { return frame_idx_; }
+  int Width() const { return width_; }
+  int Height() const { return height_; }
+  size_t SceneBytes() const { return scene_bytes_; }
+  const std::string& Error() const { return err_; }
+
+ private:
+  int RenderBatch(uint32_t n_frames);
+  void FreeState();
+  Impl* impl_{nullptr};
+  rt2_config cfg_{};
+  CameraParams cam_params_{};
+  rt2_camera camera_{};
+  int width_{0}, height_{0};
+  int frames_per_batch_{1};
+  int sm_count_{0};
+  uint64_t frame_idx_{0};
+  uint64_t launches_{0};
+  double gpu_ms_total_{0};
+  double prof_ms_[4]{0, 0, 0, 0};
+  bool profiling_{false};
+  bool timing_pending_{false};
+  size_t prof_used_{0};
+  size_t scene_bytes_{0};
+  std::string err_;
+};
+
+int DeviceCount();
+
+}  // namespace rt2

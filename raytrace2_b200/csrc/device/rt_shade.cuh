@@ -1,0 +1,142 @@
+// Materials, textures and Perlin noise on the device: replaces Material<T>::Scatter/Emit (src/cpu_raytrace/Material.cpp),
+// texture::*::Value (Texture.cpp) and PerlinNoiseGen (PerlinNoiseGen.cpp).  Shading consumes random numbers, so parity
+// with the reference is statistical; plain (FMA-contracted) float arithmetic is used here.
+#pragma once
+#include "rt_trace.cuh"
+
+namespace rt2dev {
+
+// PerlinInterp (PerlinNoiseGen.cpp:10-26)
+__device__ __forceinline__ float perlin_noise(const rt2_perlin* __restrict__ P, F3 p) {
+  float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+  float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+  int i = static_cast<int>(fx), j = static_cast<int>(fy), k = static_cast<int>(fz);
+  float uu = u * u * (3.0f - 2.0f * u);
+  float vv = v * v * (3.0f - 2.0f * v);
+  float ww = w * w * (3.0f - 2.0f * w);
+  float accum = 0.0f;
+#pragma unroll
+  for (int di = 0; di < 2; di++) {
+    const int px = __ldg(&P->perm_x[(i + di) & 255]);
+#pragma unroll
+    for (int dj = 0; dj < 2; dj++) {
+      const int py = __ldg(&P->perm_y[(j + dj) & 255]);
+#pragma unroll
+      for (int dk = 0; dk < 2; dk++) {
+        const int pz = __ldg(&P->perm_z[(k + dk) & 255]);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(&P->vec[(px ^ py ^ pz) & 255][0]));
+        float wx = u - di, wy = v - dj, wz = w - dk;
+        float weight = (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww);
+        accum += weight * ((c.x * wx + c.y * wy) + c.z * wz);
+      }
+    }
+  }
+  return accum;
+}
+
+// PerlinNoiseGen::Turb(p, 7) (PerlinNoiseGen.cpp:52-64)
+__device__ __forceinline__ float perlin_turb(const rt2_perlin* __restrict__ P, F3 p) {
+  float accum = 0.0f, weight = 1.0f;
+  for (int i = 0; i < 7; i++) {
+    accum += weight * perlin_noise(P, p);
+    weight *= 0.5f;
+    p = {p.x * 2.0f, p.y * 2.0f, p.z * 2.0f};
+  }
+  return fabsf(accum);
+}
+
+// texture::{SolidColor,Checker,Noise}::Value (Texture.hpp:14-17, Texture.cpp:7-22).  Checker recursion through texture
+// indices is followed for at most 8 levels (the reference would recurse forever on a cycle).
+__device__ __forceinline__ F3 texture_value(const DeviceScene& S, uint32_t tex_idx, F3 p) {
+  for (int depth = 0; depth < 8; depth++) {
+    const float4 t0 = __ldg(S.textures + 3 * tex_idx), t1 = __ldg(S.textures + 3 * tex_idx + 1);
+    const uint32_t type = __float_as_uint(t0.x);
+    if (type == RT2_TEX_CHECKER) {
+      // glm::ivec3 i = glm::floor(inv_scale * p); (i.x + i.y + i.z) % 2 == 0 ? even : odd
+      int ix = static_cast<int>(floorf(t1.w * p.x)), iy = static_cast<int>(floorf(t1.w * p.y)), iz = static_cast<int>(floorf(t1.w * p.z));
+      tex_idx = ((ix + iy + iz) % 2 == 0) ? __float_as_uint(t0.y) : __float_as_uint(t0.z);
+      continue;
+    }
+    if (type == RT2_TEX_NOISE) {
+      const float4 t2 = __ldg(S.textures + 3 * tex_idx + 2);
+      const rt2_perlin* P = S.perlin + __float_as_uint(t0.w);
+      float f;
+      if (__float_as_uint(t2.x) == 0u) {  // NoiseType::kPerlin
+        f = 0.5f * (1.0f + perlin_noise(P, F3{t1.w * p.x, t1.w * p.y, t1.w * p.z}));
+      } else {  // kMarble
+        f = 0.5f * (1.0f + sinf(t1.w * p.z + 10.0f * perlin_turb(P, p)));
+      }
+      return {t1.x * f, t1.y * f, t1.z * f};
+    }
+    return {t1.x, t1.y, t1.z};  // solid colour
+  }
+  return {0.0f, 0.0f, 0.0f};
+}
+
+// math::NearZero (Math.hpp:61-64): |v_i| < 1e-8 (double literal)  <=>  |v_i| <= float(1e-8)
+__device__ __forceinline__ bool near_zero(F3 v) {
+  const float e = 9.99999993922529e-09f;
+  return fabsf(v.x) <= e && fabsf(v.y) <= e && fabsf(v.z) <= e;
+}
+__device__ __forceinline__ float dot3(F3 a, F3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ F3 normalize3(F3 v) {
+  float s = 1.0f / sqrtf(dot3(v, v));
+  return {v.x * s, v.y * s, v.z * s};
+}
+// math::Reflect (Math.hpp:66)
+__device__ __forceinline__ F3 reflect3(F3 v, F3 n) {
+  float k = 2.0f * dot3(v, n);
+  return {v.x - k * n.x, v.y - k * n.y, v.z - k * n.z};
+}
+// math::Refract (Math.hpp:68-73)
+__device__ __forceinline__ F3 refract3(F3 uv, F3 n, float eta) {
+  float cos_theta = fminf(dot3(vneg(uv), n), 1.0f);
+  F3 perp = {eta * (uv.x + cos_theta * n.x), eta * (uv.y + cos_theta * n.y), eta * (uv.z + cos_theta * n.z)};
+  float k = -sqrtf(fabsf(1.0f - dot3(perp, perp)));
+  return {perp.x + k * n.x, perp.y + k * n.y, perp.z + k * n.z};
+}
+
+// Material<T>::Scatter for the scattering types.  Returns the attenuation; `dir` is the new direction (origin = hit
+// point, time unchanged).  r = the bounce's scatter draw (x,y: unit vector, z: dielectric xi).
+template <int kType>
+__device__ __forceinline__ F3 scatter(const DeviceScene& S, const float4 m0, const float4 m1, F3 d_in, F3 p, F3 n, bool front_face,
+                                      const uint4 r, F3& dir) {
+  if (kType == RT2_MAT_LAMBERTIAN || kType == RT2_MAT_TEXTURE) {
+    // Material.cpp:47-69
+    F3 u = unit_vector(u01(r.x), u01(r.y));
+    dir = {n.x + u.x, n.y + u.y, n.z + u.z};
+    if (near_zero(dir)) dir = n;
+    if (kType == RT2_MAT_LAMBERTIAN) return {m1.x, m1.y, m1.z};
+    return texture_value(S, __float_as_uint(m0.y), p);
+  }
+  if (kType == RT2_MAT_METAL) {
+    // Material.cpp:10-17: always scatters (no dot(scattered, normal) > 0 test)
+    F3 u = unit_vector(u01(r.x), u01(r.y));
+    F3 refl = normalize3(reflect3(d_in, n));
+    dir = {refl.x + m0.z * u.x, refl.y + m0.z * u.y, refl.z + m0.z * u.z};
+    return {m1.x, m1.y, m1.z};
+  }
+  if (kType == RT2_MAT_DIELECTRIC) {
+    // Material.cpp:29-45
+    float ri = front_face ? (1.0f / m0.w) : m0.w;
+    F3 unit_dir = normalize3(d_in);
+    float cos_theta = fminf(dot3(vneg(unit_dir), n), 1.0f);
+    float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    bool cannot_refract = ri * sin_theta > 1.0f;
+    float r0 = (1.0f - ri) / (1.0f + ri);
+    r0 = r0 * r0;
+    float om = 1.0f - cos_theta;
+    float schlick = r0 + (1.0f - r0) * (om * om * om * om * om);
+    if (cannot_refract || schlick > u01(r.z)) {
+      dir = reflect3(unit_dir, n);
+    } else {
+      dir = refract3(unit_dir, n, ri);
+    }
+    return {1.0f, 1.0f, 1.0f};
+  }
+  // RT2_MAT_ISOTROPIC, Material.cpp:76-83
+  dir = unit_vector(u01(r.x), u01(r.y));
+  return texture_value(S, __float_as_uint(m0.y), p);
+}
+
+}  // namespace rt2dev

@@ -1,0 +1,398 @@
+// Closest-hit query on the flattened scene: replaces the reference's Hittable::Hit tree
+// (BVHNode -> HittableList -> TransformedHittable -> Sphere / Quad / ConstantMedium).
+//
+// Contract: the result is the arg-min over all leaves of the RAW reported t, each leaf tested with the
+// reference's own interval semantics (sphere: open, Sphere.cpp:21; quad: closed, Quad.cpp:27), instanced leaves report
+// t in model units because TransformedHittable normalises the model-space direction but forwards ray_t unchanged
+// (Transform.cpp:13-20,75-88).  Constant media are sampled after the surface traversal against the current best t,
+// which is distributionally identical to the reference's in-traversal sampling — including the double
+// draw for media that sit in a span-1 BVH leaf of the reference (Q2, BVH.cpp:18-20).
+#pragma once
+#include "../../../include/rt2.h"
+#include "rt_math.cuh"
+
+namespace rt2dev {
+
+struct DeviceScene {
+  const float4* __restrict__ spheres;    // 2 x float4 per sphere  {c0.xyz, r} {disp.xyz, mat}
+  const float4* __restrict__ quads;      // 5 x float4 per quad    {n.xyz, d} {q.xyz, mat} {u} {v} {w}
+  const float4* __restrict__ xforms;     // 6 x float4 per level   inv rows 0..2, model rows 0..2
+  const uint4* __restrict__ instances;   // {chain_first, chain_len, blas_root, top_level}
+  const uint4* __restrict__ media;       // 2 x uint4 per medium
+  const float4* __restrict__ materials;  // 2 x float4 per material
+  const float4* __restrict__ textures;   // 3 x float4 per texture
+  const rt2_perlin* __restrict__ perlin;
+  const uint32_t* __restrict__ prim_refs;
+  const float4* __restrict__ nodes;  // 4 x float4 per node pair
+  uint32_t tlas_root;
+  uint32_t n_media;
+  uint32_t n_instances;
+  float min_inv_scale;
+  float background[3];
+};
+
+constexpr float kFltMax = 3.402823466e+38f;  // kInfinity (Defs.hpp:17)
+constexpr uint32_t kStackSentinel = 0x7FFFFFFFu;
+constexpr uint32_t kLeafFlag = 0x80000000u;
+constexpr int kStackSize = 64;
+
+struct RaySpace {
+  F3 o, d;
+};
+
+// TransformedHittable::WorldToModel (Transform.cpp:13-20) for one chain level.
+template <class M> __device__ __forceinline__ RaySpace world_to_model(const float4* __restrict__ x, RaySpace r) {
+  const float4 r0 = __ldg(x + 0), r1 = __ldg(x + 1), r2 = __ldg(x + 2);
+  RaySpace m;
+  // vec3(inv_model * vec4(o, 1)) : (m0*x + m1*y) + (m2*z + m3*1)
+  m.o.x = M::add(M::add(M::mul(r0.x, r.o.x), M::mul(r0.y, r.o.y)), M::add(M::mul(r0.z, r.o.z), r0.w));
+  m.o.y = M::add(M::add(M::mul(r1.x, r.o.x), M::mul(r1.y, r.o.y)), M::add(M::mul(r1.z, r.o.z), r1.w));
+  m.o.z = M::add(M::add(M::mul(r2.x, r.o.x), M::mul(r2.y, r.o.y)), M::add(M::mul(r2.z, r.o.z), r2.w));
+  // normalize(mat3(inv_model) * d) : (m0*x + m1*y) + m2*z
+  F3 v;
+  v.x = M::add(M::add(M::mul(r0.x, r.d.x), M::mul(r0.y, r.d.y)), M::mul(r0.z, r.d.z));
+  v.y = M::add(M::add(M::mul(r1.x, r.d.x), M::mul(r1.y, r.d.y)), M::mul(r1.z, r.d.z));
+  v.z = M::add(M::add(M::mul(r2.x, r.d.x), M::mul(r2.y, r.d.y)), M::mul(r2.z, r.d.z));
+  m.d = vnormalize<M>(v);
+  return m;
+}
+template <class M>
+__device__ __forceinline__ RaySpace to_chain_space(const DeviceScene& S, uint32_t chain_first, uint32_t chain_len, RaySpace r) {
+  for (uint32_t l = 0; l < chain_len; l++) r = world_to_model<M>(S.xforms + (chain_first + l) * 6, r);
+  return r;
+}
+// TransformedHittable::Hit epilogue (Transform.cpp:85-86), innermost level first.
+template <class M>
+__device__ __forceinline__ void chain_to_world(const DeviceScene& S, uint32_t chain_first, uint32_t chain_len, F3& p, F3& n) {
+  for (uint32_t l = chain_len; l-- > 0;) {
+    const float4* x = S.xforms + (chain_first + l) * 6;
+    const float4 i0 = __ldg(x + 0), i1 = __ldg(x + 1), i2 = __ldg(x + 2);
+    const float4 m0 = __ldg(x + 3), m1 = __ldg(x + 4), m2 = __ldg(x + 5);
+    F3 q;
+    q.x = M::add(M::add(M::mul(m0.x, p.x), M::mul(m0.y, p.y)), M::add(M::mul(m0.z, p.z), m0.w));
+    q.y = M::add(M::add(M::mul(m1.x, p.x), M::mul(m1.y, p.y)), M::add(M::mul(m1.z, p.z), m1.w));
+    q.z = M::add(M::add(M::mul(m2.x, p.x), M::mul(m2.y, p.y)), M::add(M::mul(m2.z, p.z), m2.w));
+    p = q;
+    // normal_mat = mat3(transpose(inverse(model))): (N*n)_r = (inv[0][r]*nx + inv[1][r]*ny) + inv[2][r]*nz
+    F3 v;
+    v.x = M::add(M::add(M::mul(i0.x, n.x), M::mul(i1.x, n.y)), M::mul(i2.x, n.z));
+    v.y = M::add(M::add(M::mul(i0.y, n.x), M::mul(i1.y, n.y)), M::mul(i2.y, n.z));
+    v.z = M::add(M::add(M::mul(i0.z, n.x), M::mul(i1.z, n.y)), M::mul(i2.z, n.z));
+    n = vnormalize<M>(v);
+  }
+}
+
+// Sphere::Hit (Sphere.cpp:7-26): returns true and the root in the OPEN interval (tmin, tmax).
+template <class M>
+__device__ __forceinline__ bool sphere_hit(const float4 s0, const float4 s1, F3 o, F3 d, float a, float time, float tmin,
+                                           float tmax, float& t_out) {
+  F3 center = ray_at<M>(make_f3(s0), make_f3(s1), time);  // center_displacement.At(r.time)
+  F3 oc = vsub<M>(center, o);
+  float h = vdot<M>(d, oc);
+  float c = M::sub(vdot<M>(oc, oc), M::mul(s0.w, s0.w));
+  float disc = M::sub(M::mul(h, h), M::mul(a, c));
+  if (disc < 0.0f) return false;
+  float sqrtd = M::sqrt(disc);
+  float root = M::div(M::sub(h, sqrtd), a);
+  if (!(tmin < root && root < tmax)) {
+    root = M::div(M::add(h, sqrtd), a);
+    if (!(tmin < root && root < tmax)) return false;
+  }
+  t_out = root;
+  return true;
+}
+
+// Quad::Hit (Quad.cpp:19-35): CLOSED interval [tmin, tmax], alpha/beta in closed [0,1].
+template <class M>
+__device__ __forceinline__ bool quad_hit(const float4* __restrict__ q, F3 o, F3 d, float tmin, float tmax, float& t_out) {
+  const float4 nd = __ldg(q + 0);
+  F3 normal = make_f3(nd);
+  float ndd = vdot<M>(normal, d);
+  // std::fabs(n_dot_raydir) < 1e-8 with a double literal  <=>  |x| <= float(1e-8)
+  if (fabsf(ndd) <= 9.99999993922529e-09f) return false;
+  float t = M::div(M::sub(nd.w, vdot<M>(normal, o)), ndd);
+  if (!(tmin <= t && t <= tmax)) return false;
+  const float4 qq = __ldg(q + 1), uu = __ldg(q + 2), vv = __ldg(q + 3), ww = __ldg(q + 4);
+  F3 p = ray_at<M>(o, d, t);
+  F3 ph = vsub<M>(p, make_f3(qq));
+  float alpha = vdot<M>(make_f3(ww), vcross<M>(ph, make_f3(vv)));
+  float beta = vdot<M>(make_f3(ww), vcross<M>(make_f3(uu), ph));
+  if (!(0.0f <= alpha && alpha <= 1.0f) || !(0.0f <= beta && beta <= 1.0f)) return false;
+  t_out = t;
+  return true;
+}
+
+struct Closest {
+  float t;
+  uint32_t prim;      // RT2 prim ref, RT2_PRIM_NONE = miss
+  int32_t instance;   // flattened instance index, -1 = world space
+};
+
+// HittableList::Hit over a short list of surface primitives (HittableList.cpp:8-22): shrinking tmax, later closed-
+// interval ties win.  Used for medium boundaries.
+template <class M>
+__device__ __forceinline__ bool list_hit(const DeviceScene& S, uint32_t first, uint32_t count, F3 o, F3 d, float a, float time,
+                                         float tmin, float tmax, float& t_out) {
+  bool any = false;
+  for (uint32_t i = 0; i < count; i++) {
+    uint32_t ref = __ldg(S.prim_refs + first + i);
+    uint32_t idx = RT2_PRIM_INDEX(ref);
+    float t;
+    bool h;
+    if (RT2_PRIM_TYPE(ref) == RT2_PRIM_SPHERE) {
+      h = sphere_hit<M>(__ldg(S.spheres + 2 * idx), __ldg(S.spheres + 2 * idx + 1), o, d, a, time, tmin, tmax, t);
+    } else {
+      h = quad_hit<M>(S.quads + 5 * idx, o, d, tmin, tmax, t);
+    }
+    if (h) {
+      any = true;
+      tmax = t;
+      t_out = t;
+    }
+  }
+  return any;
+}
+
+// Surface traversal: two-level BVH (world TLAS whose instance leaves enter a per-instance BLAS), one loop, explicit
+// stack.  Box tests only cull; they are made conservative (see cull_scale) so the result is the exact arg-min.
+template <class M>
+__device__ __forceinline__ void trace_surfaces(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, float tmax,
+                                               Closest& best) {
+  uint32_t stack[kStackSize];
+  int sp = 0;
+  best.t = tmax;
+  best.prim = RT2_PRIM_NONE;
+  best.instance = -1;
+
+  F3 o = wo, d = wd;
+  float a = vdot<M>(d, d);
+  // An instanced leaf reports t in model units (= world t * |M^-1 d|), so a world-space box at parameter t_w can hold
+  // an instanced hit with raw t as small as t_w * sigma_min * |d|: scale the culling bound accordingly.
+  float cull_scale = 1.0f;
+  if (S.n_instances > 0) cull_scale = fmaxf(1.0f, 1.0f / (S.min_inv_scale * sqrtf(a)));
+  float cur_cull = cull_scale;
+  int32_t cur_inst = -1;
+  F3 inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+  F3 oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
+
+  uint32_t cur = S.tlas_root;  // interior entry = node-pair index
+  while (true) {
+    if (!(cur & kLeafFlag)) {
+      const float4* np = S.nodes + static_cast<size_t>(cur) * 4;
+      const float4 a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
+      const float bound = best.t * cur_cull;
+      // child 0
+      float t0x = fmaf(a0.x, inv.x, oid.x), t1x = fmaf(a1.x, inv.x, oid.x);
+      float t0y = fmaf(a0.y, inv.y, oid.y), t1y = fmaf(a1.y, inv.y, oid.y);
+      float t0z = fmaf(a0.z, inv.z, oid.z), t1z = fmaf(a1.z, inv.z, oid.z);
+      float near0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+      float far0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+      bool h0 = (near0 * 0.9999995f <= far0 * 1.0000005f) && (near0 * 0.9999995f <= bound);
+      // child 1
+      t0x = fmaf(b0.x, inv.x, oid.x), t1x = fmaf(b1.x, inv.x, oid.x);
+      t0y = fmaf(b0.y, inv.y, oid.y), t1y = fmaf(b1.y, inv.y, oid.y);
+      t0z = fmaf(b0.z, inv.z, oid.z), t1z = fmaf(b1.z, inv.z, oid.z);
+      float near1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+      float far1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+      bool h1 = (near1 * 0.9999995f <= far1 * 1.0000005f) && (near1 * 0.9999995f <= bound);
+
+      const uint32_t c0 = __float_as_uint(a1.w), c1 = __float_as_uint(b1.w);
+      // entry: interior -> child pair index; leaf -> flag | (count-1) << 27 | first
+      uint32_t e0 = c0 ? (kLeafFlag | ((c0 - 1u) << 27) | __float_as_uint(a0.w)) : __float_as_uint(a0.w);
+      uint32_t e1 = c1 ? (kLeafFlag | ((c1 - 1u) << 27) | __float_as_uint(b0.w)) : __float_as_uint(b0.w);
+      if (h0 && h1) {
+        bool swap = near1 < near0;
+        cur = swap ? e1 : e0;
+        stack[sp++] = swap ? e0 : e1;
+        continue;
+      }
+      if (h0) {
+        cur = e0;
+        continue;
+      }
+      if (h1) {
+        cur = e1;
+        continue;
+      }
+    } else {
+      const uint32_t first = cur & 0x07FFFFFFu;
+      const uint32_t count = ((cur >> 27) & 0xFu) + 1u;
+      bool entered = false;
+      for (uint32_t i = 0; i < count; i++) {
+        const uint32_t ref = __ldg(S.prim_refs + first + i);
+        const uint32_t type = RT2_PRIM_TYPE(ref), idx = RT2_PRIM_INDEX(ref);
+        if (type == RT2_PRIM_SPHERE) {
+          float t;
+          if (sphere_hit<M>(__ldg(S.spheres + 2 * idx), __ldg(S.spheres + 2 * idx + 1), o, d, a, time, tmin, best.t, t)) {
+            best.t = t;
+            best.prim = ref;
+            best.instance = cur_inst;
+          }
+        } else if (type == RT2_PRIM_QUAD) {
+          float t;
+          if (quad_hit<M>(S.quads + 5 * idx, o, d, tmin, best.t, t)) {
+            best.t = t;
+            best.prim = ref;
+            best.instance = cur_inst;
+          }
+        } else {
+          // instance leaf (always a singleton leaf of the TLAS): enter its BLAS in model space
+          const uint4 in = __ldg(S.instances + idx);
+          RaySpace ms = to_chain_space<M>(S, in.x, in.y, RaySpace{wo, wd});
+          o = ms.o;
+          d = ms.d;
+          a = vdot<M>(d, d);
+          inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+          oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
+          cur_inst = static_cast<int32_t>(idx);
+          cur_cull = 1.0f;
+          stack[sp++] = kStackSentinel;
+          cur = in.z;
+          entered = true;
+        }
+      }
+      if (entered) continue;
+    }
+    // pop
+    bool done = false;
+    while (true) {
+      if (sp == 0) {
+        done = true;
+        break;
+      }
+      cur = stack[--sp];
+      if (cur != kStackSentinel) break;
+      // leave the instance: back to the world-space ray
+      o = wo;
+      d = wd;
+      a = vdot<M>(d, d);
+      inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+      oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
+      cur_inst = -1;
+      cur_cull = cull_scale;
+    }
+    if (done) break;
+  }
+}
+
+// ConstantMedium::Hit (ConstantMedium.cpp:14-58) for medium m against the current best t.  `xi` is the uniform draw.
+template <class M>
+__device__ __forceinline__ bool medium_sample(const DeviceScene& S, const uint4 m0, const uint4 m1, F3 o, F3 d, float time,
+                                              float tmin, float tmax, float xi, float& t_out) {
+  const float a = vdot<M>(d, d);
+  float t1, t2;
+  // boundary_->Hit(r, Interval::kUniverse, rec1)
+  if (!list_hit<M>(S, m0.z, m0.w, o, d, a, time, -kFltMax, kFltMax, t1)) return false;
+  // boundary_->Hit(r, Interval(rec1.t + 0.0001, kInfinity), rec2): the sum is formed in double, then stored as float
+  const float t1_eps = static_cast<float>(static_cast<double>(t1) + 0.0001);
+  if (!list_hit<M>(S, m0.z, m0.w, o, d, a, time, t1_eps, kFltMax, t2)) return false;
+  t1 = fmaxf(t1, tmin);
+  t2 = fminf(t2, tmax);
+  if (t1 >= t2) return false;
+  t1 = fmaxf(t1, 0.0f);
+  const float ray_len = M::sqrt(a);  // glm::length
+  const float dist_inside = M::mul(M::sub(t2, t1), ray_len);
+  const float hit_dist = M::mul(__uint_as_float(m0.x), logf(xi));
+  if (hit_dist > dist_inside) return false;
+  t_out = M::add(t1, M::div(hit_dist, ray_len));
+  (void)m1;
+  return true;
+}
+
+struct HitOut {
+  F3 p;
+  float t;
+  F3 n;
+  int32_t material;  // -1 = miss
+  bool front_face;
+  uint32_t prim;
+  int32_t instance;
+};
+
+// Full closest-hit query ≡ scene.hittable_list.Hit(r, Interval{tmin, tmax}, rec) (RayTracer.cpp:25).
+template <class M>
+__device__ __forceinline__ void closest_hit(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, float tmax,
+                                            const RngKey& key, uint32_t bounce, bool skip_media, HitOut& out) {
+  Closest best;
+  trace_surfaces<M>(S, wo, wd, time, tmin, tmax, best);
+
+  // constant media (few per scene): each draws its free path against the current best raw t
+  int32_t medium_hit = -1;
+  if (!skip_media) {
+    for (uint32_t m = 0; m < S.n_media; m++) {
+      const uint4 m0 = __ldg(S.media + 2 * m), m1 = __ldg(S.media + 2 * m + 1);
+      RaySpace rs = to_chain_space<M>(S, m1.x, m1.y, RaySpace{wo, wd});
+      const uint4 r = rng_draw(key, bounce, kStreamMedium + m);
+      float t;
+      if (medium_sample<M>(S, m0, m1, rs.o, rs.d, time, tmin, best.t, u01(r.x), t)) {
+        best.t = t;
+        medium_hit = static_cast<int32_t>(m);
+      }
+      if (m1.z) {  // span-1 leaf of the reference BVH: Hit() runs twice, the second against the shrunken interval
+        if (medium_sample<M>(S, m0, m1, rs.o, rs.d, time, tmin, best.t, u01(r.y), t)) {
+          best.t = t;
+          medium_hit = static_cast<int32_t>(m);
+        }
+      }
+    }
+  }
+
+  out.t = best.t;
+  out.prim = best.prim;
+  out.instance = best.instance;
+  if (medium_hit >= 0) {
+    const uint4 m0 = __ldg(S.media + 2 * medium_hit), m1 = __ldg(S.media + 2 * medium_hit + 1);
+    RaySpace rs = to_chain_space<M>(S, m1.x, m1.y, RaySpace{wo, wd});
+    F3 p = ray_at<M>(rs.o, rs.d, best.t);
+    F3 n = {1.0f, 0.0f, 0.0f};  // "both arbitrary", ConstantMedium.cpp:52-53
+    chain_to_world<M>(S, m1.x, m1.y, p, n);
+    out.p = p;
+    out.n = n;
+    out.front_face = true;
+    out.material = static_cast<int32_t>(m0.y);
+    out.prim = (RT2_PRIM_MEDIUM << 28) | static_cast<uint32_t>(medium_hit);
+    out.instance = -1;
+    return;
+  }
+  if (best.prim == RT2_PRIM_NONE) {
+    out.material = -1;
+    out.p = {0, 0, 0};
+    out.n = {0, 0, 0};
+    out.front_face = false;
+    out.t = 0.0f;
+    return;
+  }
+  // rebuild the winner's record in its own space with the reference's arithmetic, then map to world
+  RaySpace rs{wo, wd};
+  uint32_t chain_first = 0, chain_len = 0;
+  if (best.instance >= 0) {
+    const uint4 in = __ldg(S.instances + best.instance);
+    chain_first = in.x;
+    chain_len = in.y;
+    rs = to_chain_space<M>(S, chain_first, chain_len, rs);
+  }
+  const uint32_t idx = RT2_PRIM_INDEX(best.prim);
+  F3 p = ray_at<M>(rs.o, rs.d, best.t);
+  F3 outward;
+  uint32_t mat;
+  if (RT2_PRIM_TYPE(best.prim) == RT2_PRIM_SPHERE) {
+    const float4 s0 = __ldg(S.spheres + 2 * idx), s1 = __ldg(S.spheres + 2 * idx + 1);
+    F3 center = ray_at<M>(make_f3(s0), make_f3(s1), time);
+    outward = vdivs<M>(vsub<M>(p, center), s0.w);  // Sphere.cpp:32
+    mat = __float_as_uint(s1.w);
+  } else {
+    const float4 nd = __ldg(S.quads + 5 * idx), qq = __ldg(S.quads + 5 * idx + 1);
+    outward = make_f3(nd);
+    mat = __float_as_uint(qq.w);
+  }
+  // HitRecord::SetFaceNormal (HitRecord.hpp:17-20)
+  bool ff = vdot<M>(rs.d, outward) < 0.0f;
+  F3 n = ff ? outward : vneg(outward);
+  chain_to_world<M>(S, chain_first, chain_len, p, n);
+  out.p = p;
+  out.n = n;
+  out.front_face = ff;
+  out.material = static_cast<int32_t>(mat);
+}
+
+}  // namespace rt2dev

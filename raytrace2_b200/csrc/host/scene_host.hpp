@@ -1,0 +1,75 @@
+// Host scene compiler: JSON scene (current + legacy format) -> scene graph -> flat SoA buffers + BVH.
+// Replaces serialize::SceneLoader::LoadScene (src/Serialize.cpp:199-360) and the BVH wrap of App::Run
+// (src/App.cpp:126).  See scene_host.cpp for the per-step reference citations.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../../include/rt2.h"
+#include "hostmath.hpp"
+
+namespace rt2 {
+
+// Camera parameters as the loader sets them (Serialize.cpp:32-40, Camera.hpp:113-131).
+struct CameraParams {
+  V3 center{0, 0, 0};
+  V3 look_at{0, 0, -1};
+  V3 view_up{0, 1, 0};
+  float vfov{90.f};
+  float defocus_angle{0};
+  float focus_dist{10};
+};
+
+struct HostScene {
+  std::vector<rt2_sphere> spheres;
+  std::vector<rt2_quad> quads;
+  std::vector<rt2_xform> xforms;
+  std::vector<rt2_instance> instances;
+  std::vector<rt2_medium> media;
+  std::vector<rt2_material> materials;
+  std::vector<rt2_texture> textures;
+  std::vector<rt2_perlin> perlin;
+  std::vector<uint32_t> prim_refs;
+  std::vector<rt2_bvh_node> nodes;  // 2 per pair
+  uint32_t tlas_root{0};
+  uint32_t n_top_level{0};
+  std::vector<uint8_t> span1_flags;  // per top-level node (Q2)
+  float background[3]{1, 1, 1};
+  float min_inv_scale{1.f};
+  int width{1600}, height{900};
+  CameraParams cam;
+  rt2_camera camera_block{};
+  std::vector<std::string> warnings;
+
+  void FillDesc(rt2_scene_desc* d) const;
+  void UpdateCamera();  // Camera::Update, Camera.hpp:16-48
+};
+
+// Returns RT2_OK or a negative RT2_ERR_*; `err` gets a one-line reason.
+int LoadSceneFile(const std::string& path, const std::string& data_dir, uint64_t perlin_seed, HostScene* out,
+                  std::string* err);
+int LoadSceneString(const std::string& text, const std::string& data_dir, uint64_t perlin_seed, HostScene* out,
+                    std::string* err);
+int MakeSyntheticSpheres(uint32_t n, uint64_t seed, int width, int height, HostScene* out, std::string* err);
+
+// AppSettings (src/Settings.hpp:5-11, Serialize.cpp:56-65)
+struct AppSettings {
+  bool render_once{false};
+  bool save_after_render_once{false};
+  size_t num_samples{1};
+  size_t max_depth{50};
+  bool render_window{true};
+};
+int LoadAppSettings(const std::string& path, AppSettings* out, std::string* err);
+
+// BVH builder over (box, ref) leaves; appends node pairs to scene.nodes and refs to scene.prim_refs; returns the
+// root pair index.
+struct BuildPrim {
+  float bmin[3];
+  float bmax[3];
+  uint32_t ref;
+};
+uint32_t BuildBVH(std::vector<BuildPrim>& prims, HostScene* scene);
+
+}  // namespace rt2

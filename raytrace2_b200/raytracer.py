@@ -1,0 +1,297 @@
+"""Host-side mirror of the reference's renderer interface over the C ABI (include/rt2.h).
+
+Reference interfaces mirrored (paths relative to the reference root):
+  * ``serialize::SceneLoader::LoadScene``  src/Serialize.hpp:21-22   -> :class:`SceneLoader`, :class:`Scene`
+  * ``raytrace2::cpu::RayTracer``           src/cpu_raytrace/RayTracer.hpp:15-42 -> :class:`RayTracer`
+  * ``util::WriteImage``                    src/Util.hpp:11-12        -> :func:`WriteImage`
+  * ``App::Run`` (headless branch)          src/App.cpp:81-249        -> :func:`run_app`
+Method names keep the reference's spelling so the parity tests read like the reference's call sites (src/App.cpp).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, load_library
+
+HIT_DTYPE = np.dtype([("point", np.float32, 3), ("t", np.float32), ("normal", np.float32, 3), ("material", np.int32),
+                      ("prim", np.uint32), ("instance", np.int32), ("front_face", np.uint32), ("pad", np.uint32)])
+assert HIT_DTYPE.itemsize == C.sizeof(_capi.Hit)
+
+
+def _as_np(ptr, count, struct):
+    """Copy `count` structs at `ptr` into a numpy structured array."""
+    if count == 0:
+        return np.zeros(0, dtype=np.dtype(struct))
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(struct * count)).contents).copy()
+
+
+class Scene:
+    """A compiled scene: the flattened SoA buffers + BVH the device consumes (≡ cpu::Scene after App.cpp:122-126)."""
+
+    def __init__(self, handle: int):
+        self._lib = load_library()
+        self._h = C.c_void_p(handle)
+
+    # ---- construction ----
+    @classmethod
+    def load(cls, path: str, data_dir: Optional[str] = None, perlin_seed: int = 0) -> "Scene":
+        lib = load_library()
+        h = C.c_void_p()
+        check(lib.rt2_scene_load(os.fsencode(path), os.fsencode(data_dir) if data_dir else None, perlin_seed, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_string(cls, text: str, data_dir: Optional[str] = None, perlin_seed: int = 0) -> "Scene":
+        lib = load_library()
+        h = C.c_void_p()
+        check(lib.rt2_scene_load_string(text.encode(), os.fsencode(data_dir) if data_dir else None, perlin_seed, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def synthetic_spheres(cls, n: int, seed: int = 20261018, width: int = 3840, height: int = 2160) -> "Scene":
+        lib = load_library()
+        h = C.c_void_p()
+        check(lib.rt2_scene_synthetic_spheres(n, seed, width, height, C.byref(h)))
+        return cls(h.value)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.rt2_scene_destroy(h)
+
+    # ---- inspection ----
+    @property
+    def desc(self) -> _capi.SceneDesc:
+        d = _capi.SceneDesc()
+        check(self._lib.rt2_scene_get_desc(self._h, C.byref(d)))
+        return d
+
+    @property
+    def dims(self) -> Tuple[int, int]:
+        d = self.desc
+        return d.width, d.height
+
+    def set_dims(self, width: int, height: int) -> None:
+        check(self._lib.rt2_scene_set_dims(self._h, width, height))
+
+    def spheres(self):
+        d = self.desc
+        return _as_np(d.spheres, d.n_spheres, _capi.Sphere)
+
+    def quads(self):
+        d = self.desc
+        return _as_np(d.quads, d.n_quads, _capi.Quad)
+
+    def xforms(self):
+        d = self.desc
+        return _as_np(d.xforms, d.n_xforms, _capi.Xform)
+
+    def instances(self):
+        d = self.desc
+        return _as_np(d.instances, d.n_instances, _capi.Instance)
+
+    def media(self):
+        d = self.desc
+        return _as_np(d.media, d.n_media, _capi.Medium)
+
+    def materials(self):
+        d = self.desc
+        return _as_np(d.materials, d.n_materials, _capi.Material)
+
+    def textures(self):
+        d = self.desc
+        return _as_np(d.textures, d.n_textures, _capi.Texture)
+
+    def nodes(self):
+        d = self.desc
+        return _as_np(d.nodes, 2 * d.n_node_pairs, _capi.BvhNode)
+
+    def prim_refs(self):
+        d = self.desc
+        if d.n_prim_refs == 0:
+            return np.zeros(0, np.uint32)
+        return np.ctypeslib.as_array(d.prim_refs, shape=(d.n_prim_refs,)).copy()
+
+    def span1_flags(self) -> np.ndarray:
+        n = self.desc.n_top_level
+        out = np.zeros(max(n, 1), np.uint8)
+        check(self._lib.rt2_scene_span1_flags(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out[:n]
+
+    def get_perlin(self, perlin_idx: int = 0):
+        px, py, pz = (np.zeros(256, np.int32) for _ in range(3))
+        vec = np.zeros((256, 3), np.float32)
+        check(self._lib.rt2_scene_get_perlin(self._h, perlin_idx, px.ctypes.data_as(C.c_void_p), py.ctypes.data_as(C.c_void_p),
+                                             pz.ctypes.data_as(C.c_void_p), vec.ctypes.data_as(C.c_void_p)))
+        return px, py, pz, vec
+
+    def set_perlin(self, perlin_idx: int, px, py, pz, vec) -> None:
+        px, py, pz = (np.ascontiguousarray(a, np.int32) for a in (px, py, pz))
+        vec = np.ascontiguousarray(vec, np.float32).reshape(256, 3)
+        check(self._lib.rt2_scene_set_perlin(self._h, perlin_idx, px.ctypes.data_as(C.c_void_p), py.ctypes.data_as(C.c_void_p),
+                                             pz.ctypes.data_as(C.c_void_p), vec.ctypes.data_as(C.c_void_p)))
+
+
+class SceneLoader:
+    """``serialize::SceneLoader`` (src/Serialize.hpp:21-31): ``LoadScene`` returns None where the reference returns nullopt."""
+
+    def __init__(self, data_dir: Optional[str] = None, perlin_seed: int = 0):
+        self.data_dir = data_dir
+        self.perlin_seed = perlin_seed
+
+    def LoadScene(self, filepath: str) -> Optional[Scene]:
+        try:
+            return Scene.load(filepath, self.data_dir, self.perlin_seed)
+        except _capi.Rt2Error as e:
+            # Serialize.cpp:102-104
+            print(f"Failed to parse Scene: {e.message}. {filepath}", file=sys.stderr)
+            return None
+
+
+class RayTracer:
+    """``raytrace2::cpu::RayTracer`` (src/cpu_raytrace/RayTracer.hpp:15-42) on one B200.
+
+    ``num_samples`` is ``AppSettings::num_samples`` as App.cpp:129 hands it to ``Camera::SetSamplesPerPixel``: it fixes
+    the stratification grid (sqrt(num_samples) cells per axis, RayTracer.cpp:57-60).  ``frame_offset`` / ``frame_stride``
+    select which global frames this instance traces (multi-GPU sample partition).
+    """
+
+    def __init__(self, scene: Scene, *, num_samples: int = 1, max_depth: int = 50, device: int = 0, seed: int = 0x5EED,
+                 flags: int = 0, frames_per_batch: int = 0, frame_offset: int = 0, frame_stride: int = 1,
+                 dims: Optional[Tuple[int, int]] = None):
+        self._lib = load_library()
+        self.scene = scene
+        self.max_depth = max_depth
+        cfg = _capi.Config()
+        cfg.device = device
+        cfg.width, cfg.height = dims if dims else (0, 0)
+        cfg.samples_per_pixel = num_samples
+        cfg.max_depth = max_depth
+        cfg.frames_per_batch = frames_per_batch
+        cfg.frame_offset = frame_offset
+        cfg.frame_stride = frame_stride
+        cfg.flags = flags
+        cfg.seed = seed
+        self._cfg = cfg
+        h = C.c_void_p()
+        check(self._lib.rt2_create(scene._h, C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.rt2_destroy(h)
+
+    close = __del__
+
+    # ---- the reference's public surface ----
+    def Update(self, n_frames: int = 1) -> None:
+        """RayTracer::Update (RayTracer.cpp:55-70), `n_frames` times: +1 sample per pixel each."""
+        check(self._lib.rt2_update(self._h, n_frames))
+
+    def OnResize(self, dims: Sequence[int]) -> None:
+        check(self._lib.rt2_resize(self._h, int(dims[0]), int(dims[1])))
+
+    def Reset(self) -> None:
+        check(self._lib.rt2_reset(self._h))
+
+    def FrameIdx(self) -> int:
+        v = C.c_uint64()
+        check(self._lib.rt2_frame_idx(self._h, C.byref(v)))
+        return v.value
+
+    def Dims(self) -> Tuple[int, int]:
+        w, h = C.c_int32(), C.c_int32()
+        check(self._lib.rt2_dims(self._h, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def NonConvertedPixels(self) -> np.ndarray:
+        """Mean radiance, float32 [H, W, 3], row 0 = bottom of the image (RayTracer.cpp:105-112)."""
+        w, h = self.Dims()
+        out = np.empty((h, w, 3), np.float32)
+        check(self._lib.rt2_read_mean_rgb32f(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def Pixels(self) -> np.ndarray:
+        """RGBA8 preview [H, W, 4], linear, no gamma (RayTracer.cpp:16-18,65-66)."""
+        w, h = self.Dims()
+        out = np.empty((h, w, 4), np.uint8)
+        check(self._lib.rt2_read_rgba8(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # ---- extras (test / measurement hooks) ----
+    def synchronize(self) -> None:
+        check(self._lib.rt2_synchronize(self._h))
+
+    def upload_scene(self, scene: Optional[Scene] = None) -> None:
+        check(self._lib.rt2_upload_scene(self._h, (scene or self.scene)._h))
+
+    def read_accum(self, moments: bool = False):
+        w, h = self.Dims()
+        s = np.empty((h, w, 3), np.float32)
+        ss = np.empty((h, w, 3), np.float32) if moments else None
+        check(self._lib.rt2_read_accum(self._h, s.ctypes.data_as(C.c_void_p), ss.ctypes.data_as(C.c_void_p) if moments else None))
+        return (s, ss) if moments else s
+
+    def accum_device_ptr(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_size_t()
+        check(self._lib.rt2_accum_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def set_frame_idx(self, frames: int) -> None:
+        check(self._lib.rt2_set_frame_idx(self._h, frames))
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        check(self._lib.rt2_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def set_profiling(self, enabled: bool) -> None:
+        check(self._lib.rt2_set_profiling(self._h, int(enabled)))
+
+    def stats(self) -> dict:
+        st = _capi.Stats()
+        check(self._lib.rt2_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _capi.Stats._fields_}
+
+    def intersect(self, origins, directions, times=None, tmin: float = 0.001, tmax: float = 3.402823466e+38,
+                  skip_media: bool = False) -> np.ndarray:
+        """Fixed-ray closest hit ≡ scene.hittable_list.Hit(r, Interval{tmin, tmax}) (RayTracer.cpp:25)."""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        rays = np.zeros((n, 8), np.float32)
+        rays[:, 0:3] = o
+        rays[:, 3] = 0.0 if times is None else np.asarray(times, np.float32)
+        rays[:, 4:7] = d
+        out = np.zeros(n, HIT_DTYPE)
+        check(self._lib.rt2_intersect(self._h, rays.ctypes.data_as(C.c_void_p), n, tmin, tmax, int(skip_media),
+                                      out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
+def WriteImage(pixels: np.ndarray, width: int, height: int, out_path: str, png: bool = True) -> None:
+    """``util::WriteImage(vector<vec3>, w, h, path, png)`` (src/Util.cpp:39-79): sqrt gamma, vertical flip, 8-bit RGB."""
+    px = np.ascontiguousarray(pixels, np.float32).reshape(height, width, 3)
+    check(load_library().rt2_write_image(px.ctypes.data_as(C.c_void_p), width, height, os.fsencode(out_path), int(png)))
+
+
+def tonemap_rgb8(pixels: np.ndarray) -> np.ndarray:
+    px = np.ascontiguousarray(pixels, np.float32)
+    h, w, _ = px.shape
+    out = np.empty((h, w, 3), np.uint8)
+    check(load_library().rt2_tonemap_rgb8(px.ctypes.data_as(C.c_void_p), w, h, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def run_app(argv: Sequence[str], settings_path: str, data_dir: Optional[str] = None) -> int:
+    """Headless ``App::Run`` (src/App.cpp:81-249): ``argv`` as for ``raytrace_2 [scene[.json]] [out.png]``."""
+    lib = load_library()
+    arr = (C.c_char_p * len(argv))(*[os.fsencode(a) for a in argv])
+    return lib.rt2_app_run(len(argv), arr, os.fsencode(settings_path), os.fsencode(data_dir) if data_dir else None)
