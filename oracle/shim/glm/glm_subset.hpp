@@ -277,8 +277,11 @@ template <typename T> constexpr tmat4<T> scale(const tmat4<T>& m, const tvec3<T>
 // ---- quaternion (w, x, y, z) ----
 template <typename T>
 struct tquat {
-  T x, y, z, w;  // deliberately uninitialised when default-constructed, like GLM (Serialize.cpp:114)
-  tquat() = default;
+  // GLM leaves a default-constructed quat uninitialised, and the reference reads it when a transform has no
+  // "rotation" key (Serialize.cpp:114,125) — undefined behaviour whose evident intent is "no rotation".  The oracle
+  // pins that intent: identity.
+  T x{0}, y{0}, z{0}, w{1};
+  constexpr tquat() = default;
   constexpr tquat(T ww, T xx, T yy, T zz) : x(xx), y(yy), z(zz), w(ww) {}
   constexpr tquat(T ww, const tvec3<T>& v) : x(v.x), y(v.y), z(v.z), w(ww) {}
 };

@@ -249,6 +249,7 @@ __device__ __forceinline__ void trace_surfaces(const DeviceScene& S, F3 wo, F3 w
           stack[sp++] = kStackSentinel;
           cur = in.z;
           entered = true;
+          break;  // instance references are singleton leaves (host/bvh_build.cpp)
         }
       }
       if (entered) continue;

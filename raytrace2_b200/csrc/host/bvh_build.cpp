@@ -15,7 +15,7 @@ namespace {
 
 constexpr int kBins = 16;
 constexpr uint32_t kMaxLeaf = 4;
-constexpr int kMaxDepth = 56;  // the device traversal stack holds 64 entries
+constexpr int kMaxDepth = 40;  // beyond this: median splits (<= 24 more levels for 16M prims; the device stack holds 64)
 
 struct Bounds {
   float mn[3], mx[3];
@@ -72,6 +72,10 @@ size_t Split(BuildCtx& ctx, size_t begin, size_t end, const Bounds& bounds, bool
   std::vector<BuildPrim>& p = *ctx.prims;
   const size_t n = end - begin;
   *make_leaf = false;
+  // An instance reference must sit alone in its leaf: the device traversal switches to the instance's model space
+  // when it meets one and does not come back for leaf-mates.
+  bool has_instance = false;
+  for (size_t i = begin; i < end; i++) has_instance |= (RT2_PRIM_TYPE(p[i].ref) == RT2_PRIM_INSTANCE);
   Bounds cb;
   cb.Reset();
   for (size_t i = begin; i < end; i++) {
@@ -127,7 +131,7 @@ size_t Split(BuildCtx& ctx, size_t begin, size_t end, const Bounds& bounds, bool
   if (best_axis >= 0) {
     float leaf_cost = bounds.HalfArea() * static_cast<float>(n);
     // traversal cost 1 box-pair test ~ 1.2 primitive tests
-    if (n <= kMaxLeaf && leaf_cost <= best_cost + 1.2f * bounds.HalfArea()) {
+    if (!has_instance && n <= kMaxLeaf && leaf_cost <= best_cost + 1.2f * bounds.HalfArea()) {
       *make_leaf = true;
       return begin;
     }
@@ -143,7 +147,7 @@ size_t Split(BuildCtx& ctx, size_t begin, size_t end, const Bounds& bounds, bool
     if (mid > begin && mid < end) return mid;
   }
   // all centroids coincide (or the binned split degenerated)
-  if (n <= kMaxLeaf) {
+  if (!has_instance && n <= kMaxLeaf) {
     *make_leaf = true;
     return begin;
   }
@@ -158,9 +162,6 @@ void MakeLeaf(BuildCtx& ctx, rt2_bvh_node* node, size_t begin, size_t end) {
   for (size_t i = begin; i < end; i++) ctx.sc->prim_refs.push_back((*ctx.prims)[i].ref);
 }
 
-// Fills nodes[2*pair], nodes[2*pair+1] with the two halves of [begin, end) (end - begin >= 2).
-void BuildPair(BuildCtx& ctx, uint32_t pair, size_t begin, size_t end, int depth);
-
 void BuildChild(BuildCtx& ctx, uint32_t node_idx, size_t begin, size_t end, int depth) {
   const size_t n = end - begin;
   Bounds b = RangeBounds(*ctx.prims, begin, end);
@@ -168,12 +169,13 @@ void BuildChild(BuildCtx& ctx, uint32_t node_idx, size_t begin, size_t end, int 
   size_t mid = begin;
   if (!leaf) {
     if (depth >= kMaxDepth) {
-      // depth guard: median split (or a big leaf at the very bottom) keeps the device stack bounded
-      if (depth >= kMaxDepth + 6) {
-        leaf = true;
-      } else {
-        mid = begin + n / 2;
+      // depth guard: median splits keep the device stack bounded (leaf size stays <= 16, the stack entry's limit)
+      if (n <= 2) {
+        bool inst = false;
+        for (size_t i = begin; i < end; i++) inst |= (RT2_PRIM_TYPE((*ctx.prims)[i].ref) == RT2_PRIM_INSTANCE);
+        leaf = !inst;
       }
+      mid = begin + n / 2;
     } else {
       mid = Split(ctx, begin, end, b, &leaf);
     }

@@ -1,0 +1,43 @@
+"""Deterministic fixed-ray sets for the intersection parity tests: camera rays through pixel centres
+plus rays with random origins inside the scene bounds, half unit-length and half |d| in (0.05, 2] (exercises quirk Q1)."""
+import numpy as np
+
+
+def scene_bounds(scene):
+    d = scene.desc
+    nodes = scene.nodes()
+    root = nodes[2 * d.tlas_root: 2 * d.tlas_root + 2]
+    lo = np.full(3, np.inf)
+    hi = np.full(3, -np.inf)
+    for n in root:
+        if n["bmin"][0] <= n["bmax"][0]:
+            lo = np.minimum(lo, np.array(n["bmin"]))
+            hi = np.maximum(hi, np.array(n["bmax"]))
+    return np.maximum(lo, -1500.0), np.minimum(hi, 1500.0)
+
+
+def fixed_rays(scene, n: int, seed: int):
+    rng = np.random.default_rng(seed)
+    lo, hi = scene_bounds(scene)
+    d = scene.desc
+    n_cam = n // 4
+    n_rand = n - n_cam
+    # camera rays: pixel centres, from the camera centre (no lens, no jitter)
+    cam = d.camera
+    xs = rng.integers(0, d.width, n_cam)
+    ys = rng.integers(0, d.height, n_cam)
+    p00, du, dv, c = (np.array(list(v), np.float32) for v in (cam.pixel00, cam.pixel_delta_u, cam.pixel_delta_v, cam.center))
+    pc = p00[None] + xs[:, None].astype(np.float32) * du[None] + ys[:, None].astype(np.float32) * dv[None]
+    dc = pc - c[None]
+    dc = (dc / np.linalg.norm(dc, axis=1, keepdims=True)).astype(np.float32)
+    oc = np.repeat(c[None], n_cam, 0)
+    # interior rays
+    o = rng.uniform(lo, hi, size=(n_rand, 3)).astype(np.float32)
+    v = rng.normal(size=(n_rand, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    scale = np.where(rng.random(n_rand) < 0.5, 1.0, rng.uniform(0.05, 2.0, n_rand))
+    dr = (v * scale[:, None]).astype(np.float32)
+    origins = np.concatenate([oc, o]).astype(np.float32)
+    dirs = np.concatenate([dc, dr]).astype(np.float32)
+    times = rng.random(n).astype(np.float32)
+    return origins, dirs, times
