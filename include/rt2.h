@@ -127,7 +127,7 @@ typedef struct rt2_perlin {
 
 /* BVH node, 32 bytes; nodes are stored as sibling PAIRS (64-byte aligned): pair p = nodes[2p], nodes[2p+1].
  * count == 0: interior, left_first = index of the child pair.  count > 0: leaf over prim_refs[left_first .. +count).
- * An empty slot has bmin = +inf, bmax = -inf. */
+ * An empty slot has NaN bounds (never entered by the slab test). */
 typedef struct rt2_bvh_node {
   float bmin[3];
   uint32_t left_first;

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libraytrace2_b200.so")
+LIB_PATH = os.environ.get("RT2_LIB_PATH") or os.path.join(_HERE, "lib", "libraytrace2_b200.so")
 
 RT2_OK = 0
 RT2_ERR_INVALID_ARG = -1

@@ -35,10 +35,17 @@ constexpr float kFltMax = 3.402823466e+38f;  // kInfinity (Defs.hpp:17)
 constexpr uint32_t kStackSentinel = 0x7FFFFFFFu;
 constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr int kStackSize = 64;
+#define RT2_STACK_GUARD if (sp < kStackSize)
 
 struct RaySpace {
   F3 o, d;
 };
+
+// Reciprocal direction for the slab test.  Exact zeros (and denormals) are replaced by +-1e-30 so that the fused form
+// t = b * inv - o * inv never produces inf - inf; box tests only cull, the exact Hit() arithmetic never sees this value.
+// Branch-free on purpose: a data-dependent branch here made ptxas wrap the traversal loop in extra convergence
+// barriers and halved k_extend's throughput (measured on B200, profiles/r01_notes.md).
+__device__ __forceinline__ float safe_rcp(float x) { return copysignf(__fdividef(1.0f, fmaxf(fabsf(x), 1e-30f)), x); }
 
 // TransformedHittable::WorldToModel (Transform.cpp:13-20) for one chain level.
 template <class M> __device__ __forceinline__ RaySpace world_to_model(const float4* __restrict__ x, RaySpace r) {
@@ -172,7 +179,7 @@ __device__ __forceinline__ void trace_surfaces(const DeviceScene& S, F3 wo, F3 w
   if (S.n_instances > 0) cull_scale = fmaxf(1.0f, 1.0f / (S.min_inv_scale * sqrtf(a)));
   float cur_cull = cull_scale;
   int32_t cur_inst = -1;
-  F3 inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+  F3 inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
   F3 oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
 
   uint32_t cur = S.tlas_root;  // interior entry = node-pair index
@@ -203,7 +210,7 @@ __device__ __forceinline__ void trace_surfaces(const DeviceScene& S, F3 wo, F3 w
       if (h0 && h1) {
         bool swap = near1 < near0;
         cur = swap ? e1 : e0;
-        stack[sp++] = swap ? e0 : e1;
+        RT2_STACK_GUARD stack[sp++] = swap ? e0 : e1;  // the host builder bounds the depth; never write past the stack
         continue;
       }
       if (h0) {
@@ -242,11 +249,11 @@ __device__ __forceinline__ void trace_surfaces(const DeviceScene& S, F3 wo, F3 w
           o = ms.o;
           d = ms.d;
           a = vdot<M>(d, d);
-          inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+          inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
           oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
           cur_inst = static_cast<int32_t>(idx);
           cur_cull = 1.0f;
-          stack[sp++] = kStackSentinel;
+          RT2_STACK_GUARD stack[sp++] = kStackSentinel;
           cur = in.z;
           entered = true;
           break;  // instance references are singleton leaves (host/bvh_build.cpp)
@@ -267,7 +274,7 @@ __device__ __forceinline__ void trace_surfaces(const DeviceScene& S, F3 wo, F3 w
       o = wo;
       d = wd;
       a = vdot<M>(d, d);
-      inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+      inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
       oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
       cur_inst = -1;
       cur_cull = cull_scale;

@@ -44,10 +44,11 @@ struct BuildCtx {
   HostScene* sc;
 };
 
+// An empty slot carries NaN bounds: every comparison of the device slab test is then false, so it is never entered.
 void SetEmpty(rt2_bvh_node* n) {
   for (int k = 0; k < 3; k++) {
-    n->bmin[k] = INFINITY;
-    n->bmax[k] = -INFINITY;
+    n->bmin[k] = NAN;
+    n->bmax[k] = NAN;
   }
   n->left_first = 0;
   n->count = 0;

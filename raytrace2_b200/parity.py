@@ -21,7 +21,8 @@ def z_scores(sum_a, sumsq_a, n_a, sum_b, sumsq_b, n_b):
 
 
 def tile_z_scores(sum_a, sumsq_a, n_a, sum_b, sumsq_b, n_b, tile: int = 50):
-    """z-score of tile-mean differences (tiles of `tile` x `tile` pixels, all channels pooled)."""
+    """z-scores of tile-mean differences, one per (tile, channel).  Channels are NOT pooled: the three channels of a
+    sample are strongly correlated (same path), so a pooled variance would be underestimated by up to 3x."""
     sum_a, sumsq_a, sum_b, sumsq_b = (np.asarray(x, np.float64) for x in (sum_a, sumsq_a, sum_b, sumsq_b))
     h, w, _ = sum_a.shape
     m_a, m_b = sum_a / n_a, sum_b / n_b
@@ -31,9 +32,9 @@ def tile_z_scores(sum_a, sumsq_a, n_a, sum_b, sumsq_b, n_b, tile: int = 50):
     for y in range(0, h - tile + 1, tile):
         for x in range(0, w - tile + 1, tile):
             sl = (slice(y, y + tile), slice(x, x + tile))
-            diff = (m_a[sl] - m_b[sl]).sum()
-            var = (v_a[sl] + v_b[sl]).sum()
-            out.append(diff / np.sqrt(var) if var > 0 else 0.0)
+            diff = (m_a[sl] - m_b[sl]).sum(axis=(0, 1))
+            var = (v_a[sl] + v_b[sl]).sum(axis=(0, 1))
+            out.append(np.where(var > 0, diff / np.sqrt(np.maximum(var, 1e-300)), 0.0))
     return np.array(out)
 
 

@@ -10,7 +10,7 @@ def scene_bounds(scene):
     lo = np.full(3, np.inf)
     hi = np.full(3, -np.inf)
     for n in root:
-        if n["bmin"][0] <= n["bmax"][0]:
+        if n["bmin"][0] <= n["bmax"][0]:  # skips empty slots (NaN bounds)
             lo = np.minimum(lo, np.array(n["bmin"]))
             hi = np.maximum(hi, np.array(n["bmax"]))
     return np.maximum(lo, -1500.0), np.minimum(hi, 1500.0)
@@ -41,3 +41,36 @@ def fixed_rays(scene, n: int, seed: int):
     dirs = np.concatenate([dc, dr]).astype(np.float32)
     times = rng.random(n).astype(np.float32)
     return origins, dirs, times
+
+
+def leaf_to_prim_ref(scene_json_path):
+    """Maps the CPU restatement's leaf ids (creation order of spheres / quads / box faces / medium wrappers, see
+    oracle/rt_oracle.cpp) to the product's primitive references ((type << 28) | index; include/rt2.h)."""
+    import json
+    doc = json.load(open(scene_json_path))
+    prims = doc["primitives"]
+    out = []
+    n_sph = n_quad = n_med = 0
+    if isinstance(prims, dict):  # legacy: spheres, quads, boxes in that order
+        seq = [("sphere", p) for p in prims.get("spheres", [])] + [("quad", p) for p in prims.get("quads", [])] + \
+              [("box", p) for p in prims.get("boxes", [])]
+    else:
+        seq = [(p.get("type", ""), p) for p in prims]
+    for ty, p in seq:
+        if ty == "sphere":
+            out.append((0 << 28) | n_sph)
+            n_sph += 1
+        elif ty == "quad":
+            out.append((1 << 28) | n_quad)
+            n_quad += 1
+        elif ty == "box":
+            for _ in range(6):
+                out.append((1 << 28) | n_quad)
+                n_quad += 1
+        else:
+            continue
+        cm = p.get("constant_medium")
+        if cm is not None and ("albedo" in cm or "material" in cm):
+            out.append((3 << 28) | n_med)
+            n_med += 1
+    return np.array(out + [0xFFFFFFFF], np.uint32)  # index -1 (miss) -> PRIM_NONE

@@ -75,8 +75,8 @@ def _check_bvh(scene):
         for side in range(2):
             n = nodes[2 * pair + side]
             bmin, bmax = np.array(n["bmin"]), np.array(n["bmax"])
-            if bmin[0] > bmax[0]:
-                continue  # empty slot
+            if not (bmin[0] <= bmax[0]):
+                continue  # empty slot (NaN bounds)
             if lo is not None:
                 assert np.all(bmin >= lo - 1e-3) and np.all(bmax <= hi + 1e-3), "child box must lie inside its parent"
             if n["count"] == 0:

@@ -1,0 +1,32 @@
+#!/usr/bin/env python3
+"""Quick perf probe: Mrays/s + per-kernel split for a scene at several settings."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import raytrace2_b200 as rt
+
+def run(name, spp_total, spp, fpb, flags=0, dims=None, reps=3, label=""):
+    scene = rt.Scene.load(f"data/{name}.json") if not name.startswith("synthetic:") else rt.Scene.synthetic_spheres(int(name.split(":")[1]), width=dims[0], height=dims[1])
+    tr = rt.RayTracer(scene, num_samples=spp_total, frames_per_batch=fpb, flags=flags, seed=1, dims=dims)
+    tr.Update(spp); tr.synchronize()
+    tr.Reset()
+    for _ in range(reps):
+        tr.Update(spp)
+    st = tr.stats()
+    tr.Reset(); tr.set_profiling(True); tr.Update(spp); ps = tr.stats()
+    print(f"{label or name}: spp_total={spp_total} spp={spp} fpb={fpb} flags={flags} dims={tr.Dims()} -> {st['rays']/st['gpu_ms_total']*1e-3:.1f} Mrays/s "
+          f"({st['gpu_ms_total']/reps:.2f} ms per {spp} spp, rays/path {st['rays']/st['paths']:.3f}) | profiled split ms: extend {ps['gpu_ms_extend']:.2f} shade {ps['gpu_ms_shade']:.2f} other {ps['gpu_ms_other']:.2f}", flush=True)
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "book2"
+    if which == "book2":
+        n = "book2_final_scene_10000_samples"
+        run(n, 64, 64, 0)
+        run(n, 10000, 64, 0)
+        run(n, 10000, 16, 16)
+        run(n, 64, 16, 16)
+        run(n, 64, 64, 0, flags=rt.RT2_FLAG_FAST_MATH)
+    elif which == "all":
+        for n in ["cornell_original_test", "cornell_volume_10000_samples", "book2_final_scene_10000_samples", "final_render_book_1"]:
+            run(n, 10000, 32, 0)
+            run(n, 10000, 32, 0, flags=rt.RT2_FLAG_FAST_MATH, label=n + " [fast]")
