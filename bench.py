@@ -11,7 +11,7 @@ data/book2_final_scene_10000_samples.json at its authored 600x600, max_depth 50.
 
 Rank 0 prints ONE JSON line.  `value` = rays traced by all ranks / device time (CUDA events on the launching stream, max
 over ranks) with the scene resident in HBM; `e2e` = the same metric through the public C-ABI path with host buffers: scene
-upload (H2D) + render + mean-image read-back (D2H) inside the timed region; `roofline` = the dominant kernel (k_extend)
+upload (H2D) + render + mean-image read-back (D2H) inside the timed region; `roofline` = the dominant kernel (k_traverse)
 against the measured HBM peak; `cpu_baseline` = the reference CPU renderer timed on this box's host cores (N = 1 only).
 """
 from __future__ import annotations
@@ -30,9 +30,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 DEFAULT_SCENE = "book2_final_scene_10000_samples"
-# algorithmic HBM bytes per ray of k_extend: ray origin+time 16 + direction 16 + path state 16 read,
-# hit record 32 + bin-queue index 4 written
-EXTEND_BYTES_PER_RAY = 16 + 16 + 16 + 32 + 4
+# algorithmic HBM bytes per ray of k_traverse: ray origin+time 16 + direction 16 read, closest-surface
+# record 16 written
+EXTEND_BYTES_PER_RAY = 16 + 16 + 16
 
 
 def parse_args():
@@ -286,13 +286,13 @@ def run_ours(args):
     tracer.set_profiling(False)
     peaks, peak_src = measured_peaks()
     ext_ms = ps["gpu_ms_extend"]
-    prof_total = ps["gpu_ms_extend"] + ps["gpu_ms_shade"] + ps["gpu_ms_other"]
+    prof_total = ps["gpu_ms_extend"] + ps["gpu_ms_shade"] + ps["gpu_ms_other"] + ps["gpu_ms_finish"]
     achieved = ps["rays"] * EXTEND_BYTES_PER_RAY / (ext_ms * 1e-3) * 1e-9 if ext_ms > 0 else 0.0
-    roofline = {"kernel": "k_extend", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    roofline = {"kernel": "k_traverse", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_ray": EXTEND_BYTES_PER_RAY,
                 "share_of_step": ext_ms / prof_total if prof_total > 0 else None,
-                "note": "k_extend is FP32-issue / latency bound (scene lives in L1/L2); see DESIGN.md and profiles/"}
+                "note": "k_traverse is FP32-issue / latency bound (scene lives in L1/L2); see DESIGN.md and profiles/"}
 
     line = {
         "metric": "Mrays/s", "value": rays_all / (ms_all * 1e-3) * 1e-6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,

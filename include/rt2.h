@@ -219,9 +219,15 @@ typedef struct rt2_stats {
   uint64_t frames;      /* local frames rendered since the last reset */
   uint64_t launches;    /* kernels launched since creation */
   double gpu_ms_total;  /* CUDA-event time of all rt2_update calls since the last reset */
-  double gpu_ms_extend; /* summed CUDA-event time of the extend kernel (only if profiling was enabled) */
-  double gpu_ms_shade;
-  double gpu_ms_other;
+  double gpu_ms_extend; /* summed CUDA-event time of k_traverse (only while profiling is enabled) */
+  double gpu_ms_shade;  /* ... of the shade kernels */
+  double gpu_ms_other;  /* ... of generate / accumulate / stats */
+  double gpu_ms_finish; /* ... of k_finish_hit (media + hit record + binning) */
+  /* algorithmic work done by active lanes of k_traverse while profiling is enabled */
+  uint64_t box_pair_tests; /* node-pair visits = 2 AABB slab tests each */
+  uint64_t sphere_tests;
+  uint64_t quad_tests;
+  uint64_t instance_visits;
 } rt2_stats;
 
 typedef struct rt2_hit {

@@ -102,7 +102,8 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("frames", C.c_uint64), ("launches", C.c_uint64),
                 ("gpu_ms_total", C.c_double), ("gpu_ms_extend", C.c_double), ("gpu_ms_shade", C.c_double),
-                ("gpu_ms_other", C.c_double)]
+                ("gpu_ms_other", C.c_double), ("gpu_ms_finish", C.c_double), ("box_pair_tests", C.c_uint64),
+                ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64)]
 
 
 class Hit(C.Structure):

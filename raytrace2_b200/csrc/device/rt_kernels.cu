@@ -27,7 +27,8 @@ namespace rt2dev {
 
 constexpr int kBlock = 256;
 constexpr int kNumBins = 6;  // 0 terminal (miss / light), 1 lambertian, 2 texture, 3 metal, 4 dielectric, 5 isotropic
-constexpr int kCounterStride = 8;
+constexpr int kCounterStride = 8;  // [0] queue size, [1..6] material bins, [7] traversal fetch cursor
+constexpr int kFetchThreshold = 20;  // lanes: below this a warp refills its idle lanes from the queue
 
 struct FrameParams {
   rt2_camera cam;
@@ -117,21 +118,45 @@ struct BinQueues {
   __host__ __device__ uint32_t* q(int bin) const { return base + static_cast<size_t>(bin) * stride; }
 };
 
-// Closest hit for every queued ray of this bounce; hit record out; ray index appended to its material bin.
+// Extend, part 1: closest SURFACE for every queued ray of this bounce (persistent warps, dynamic ray fetch).
+// counters[7] of the bounce is the queue's fetch cursor (zeroed with the other counters at batch start).
+template <class M, bool kCount>
+__global__ void __launch_bounds__(kBlock) k_traverse(const DeviceScene S, uint32_t* __restrict__ counters,
+                                                     const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                     uint4* __restrict__ trav, unsigned long long* __restrict__ work_counters) {
+  const uint32_t n = counters[0];
+  TravCounters cnt;
+  // scene.hittable_list.Hit(scene, r, Interval{0.001, kInfinity}, rec)  (RayTracer.cpp:25)
+  traverse_queue<M, kCount, kFetchThreshold>(S, n, ray_o, ray_d, 0.001f, kFltMax, counters + 7, trav, cnt);
+  if (kCount) {
+    // warp-reduce, one atomic per warp and counter
+    uint32_t v[4] = {cnt.box_pairs, cnt.spheres, cnt.quads, cnt.instances};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t x = v[k];
+      for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
+      if ((threadIdx.x & 31u) == 0u && x) atomicAdd(&work_counters[k], static_cast<unsigned long long>(x));
+    }
+  }
+}
+
+// Extend, part 2: constant media against the closest surface, the winner's hit record, and the push of the ray index
+// into its material bin.  One thread per ray, uniform work.
 template <class M>
-__global__ void __launch_bounds__(kBlock) k_extend(const DeviceScene S, const FrameParams fp, uint32_t bounce,
-                                                   uint32_t* __restrict__ counters, const float4* __restrict__ ray_o,
-                                                   const float4* __restrict__ ray_d, const float4* __restrict__ state,
-                                                   float4* __restrict__ hit0, float4* __restrict__ hit1, BinQueues bins) {
+__global__ void __launch_bounds__(kBlock) k_finish_hit(const DeviceScene S, const FrameParams fp, uint32_t bounce,
+                                                       uint32_t* __restrict__ counters, const float4* __restrict__ ray_o,
+                                                       const float4* __restrict__ ray_d, const float4* __restrict__ state,
+                                                       const uint4* __restrict__ trav, float4* __restrict__ hit0,
+                                                       float4* __restrict__ hit1, BinQueues bins) {
   const uint32_t n = counters[0];
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float4 o = ray_o[i], d = ray_d[i];
-    const uint32_t slot = __float_as_uint(state[i].w);
-    const RngKey key = key_of_slot(fp, slot);
+    const uint4 tr = trav[i];
+    const RngKey key = key_of_slot(fp, __float_as_uint(state[i].w));
     HitOut h;
-    // scene.hittable_list.Hit(scene, r, Interval{0.001, kInfinity}, rec)  (RayTracer.cpp:25)
-    closest_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, kFltMax, key, bounce, false, h);
+    finish_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, bounce,
+                  false, h);
     hit0[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t);
     const uint32_t mbits = (h.material < 0) ? 0xFFFFFFFFu : (static_cast<uint32_t>(h.material) | (h.front_face ? 0x80000000u : 0u));
     hit1[i] = make_float4(h.n.x, h.n.y, h.n.z, __uint_as_float(mbits));
@@ -252,17 +277,20 @@ __global__ void k_batch_stats(const uint32_t* __restrict__ counters, uint32_t ma
   }
 }
 
-// Fixed-ray parity hook (rt2_intersect): one thread per ray, full record out.
+// Fixed-ray parity hook (rt2_intersect): the same traversal (k_traverse) followed by this record writer.
 template <class M>
-__global__ void __launch_bounds__(kBlock) k_intersect(const DeviceScene S, const float4* __restrict__ rays, uint32_t n, float tmin,
-                                                      float tmax, int skip_media, uint32_t seed_lo, uint32_t seed_hi,
-                                                      rt2_hit* __restrict__ out) {
+__global__ void __launch_bounds__(kBlock) k_finish_intersect(const DeviceScene S, const float4* __restrict__ ray_o,
+                                                             const float4* __restrict__ ray_d, const uint4* __restrict__ trav, uint32_t n,
+                                                             float tmin, int skip_media, uint32_t seed_lo, uint32_t seed_hi,
+                                                             rt2_hit* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float4 o = rays[2 * i], d = rays[2 * i + 1];
+  const float4 o = ray_o[i], d = ray_d[i];
+  const uint4 tr = trav[i];
   RngKey key{i, 0u, seed_lo, seed_hi};
   HitOut h;
-  closest_hit<M>(S, make_f3(o), make_f3(d), o.w, tmin, tmax, key, 0, skip_media != 0, h);
+  finish_hit<M>(S, make_f3(o), make_f3(d), o.w, tmin, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, 0,
+                skip_media != 0, h);
   rt2_hit r;
   r.point[0] = h.p.x, r.point[1] = h.p.y, r.point[2] = h.p.z;
   r.t = h.t;
@@ -273,6 +301,15 @@ __global__ void __launch_bounds__(kBlock) k_intersect(const DeviceScene S, const
   r.front_face = h.front_face ? 1u : 0u;
   r.pad = 0;
   out[i] = r;
+}
+
+// k_traverse with caller-supplied interval and a plain count (rt2_intersect).
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_traverse_rays(const DeviceScene S, uint32_t n, uint32_t* __restrict__ cursor,
+                                                          const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float tmin,
+                                                          float tmax, uint4* __restrict__ trav) {
+  TravCounters cnt;
+  traverse_queue<M, false, kFetchThreshold>(S, n, ray_o, ray_d, tmin, tmax, cursor, trav, cnt);
 }
 
 }  // namespace rt2dev
@@ -314,6 +351,7 @@ struct Renderer::Impl {
   float4* state[2]{nullptr, nullptr};
   float4* hit0{nullptr};
   float4* hit1{nullptr};
+  uint4* trav{nullptr};
   BinQueues bins{};
   uint32_t* counters{nullptr};
   float4* radiance{nullptr};
@@ -321,9 +359,11 @@ struct Renderer::Impl {
   float4* accum_sq{nullptr};
   float* mean_rgb{nullptr};
   uchar4* rgba8{nullptr};
-  unsigned long long* totals{nullptr};
+  unsigned long long* totals{nullptr};  // [0] rays [1] paths [2..5] work counters (box pairs, spheres, quads, instances)
   cudaStream_t stream{nullptr};
   cudaEvent_t ev_start{nullptr}, ev_stop{nullptr};
+  std::vector<cudaEvent_t> timing_events;  // start/stop pairs of rt2_update calls not yet folded into gpu_ms_total
+  size_t timing_used{0};
   int grid_extend{0}, grid_stream{0};
   bool bin_present[kNumBins]{};
   std::vector<cudaEvent_t> prof_events;
@@ -344,19 +384,21 @@ Renderer::~Renderer() {
   if (m.ev_start) cudaEventDestroy(m.ev_start);
   if (m.ev_stop) cudaEventDestroy(m.ev_stop);
   for (cudaEvent_t e : m.prof_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : m.timing_events) cudaEventDestroy(e);
   if (m.stream) cudaStreamDestroy(m.stream);
   delete impl_;
 }
 
 void Renderer::FreeState() {
   Impl& m = *impl_;
-  void* bufs[] = {m.ray_o[0], m.ray_o[1], m.ray_d[0], m.ray_d[1], m.state[0], m.state[1], m.hit0, m.hit1, m.counters,
+  void* bufs[] = {m.ray_o[0], m.ray_o[1], m.ray_d[0], m.ray_d[1], m.state[0], m.state[1], m.hit0, m.hit1, m.trav, m.counters,
                   m.radiance, m.accum, m.accum_sq, m.mean_rgb, m.rgba8};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.bins.base) cudaFree(m.bins.base);
   m.bins.base = nullptr;
   m.ray_o[0] = m.ray_o[1] = m.ray_d[0] = m.ray_d[1] = m.state[0] = m.state[1] = m.hit0 = m.hit1 = nullptr;
+  m.trav = nullptr;
   m.counters = nullptr;
   m.radiance = m.accum = m.accum_sq = nullptr;
   m.mean_rgb = nullptr;
@@ -379,17 +421,17 @@ int Renderer::Init(const HostScene& scene, const rt2_config& cfg) {
   RT2_CUDA(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
   RT2_CUDA(cudaEventCreate(&m.ev_start));
   RT2_CUDA(cudaEventCreate(&m.ev_stop));
-  RT2_CUDA(cudaMalloc(&m.totals, 4 * sizeof(unsigned long long)));
-  RT2_CUDA(cudaMemset(m.totals, 0, 4 * sizeof(unsigned long long)));
+  RT2_CUDA(cudaMalloc(&m.totals, 8 * sizeof(unsigned long long)));
+  RT2_CUDA(cudaMemset(m.totals, 0, 8 * sizeof(unsigned long long)));
   if (cfg_.max_depth < 1) cfg_.max_depth = 1;
   if (cfg_.samples_per_pixel < 1) cfg_.samples_per_pixel = 1;
   if (cfg_.frame_stride < 1) cfg_.frame_stride = 1;
   // persistent grids: resident blocks per SM x SM count
   int occ = 0;
   if (cfg_.flags & RT2_FLAG_FAST_MATH) {
-    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<FastMath>, kBlock, 0));
+    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<FastMath, false>, kBlock, 0));
   } else {
-    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<ExactMath>, kBlock, 0));
+    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false>, kBlock, 0));
   }
   if (occ < 1) occ = 1;
   m.grid_extend = sm_count_ * occ;
@@ -518,6 +560,7 @@ int Renderer::Resize(int w, int h) {
   }
   RT2_CUDA(cudaMalloc(&m.hit0, N * sizeof(float4)));
   RT2_CUDA(cudaMalloc(&m.hit1, N * sizeof(float4)));
+  RT2_CUDA(cudaMalloc(&m.trav, N * sizeof(uint4)));
   RT2_CUDA(cudaMalloc(&m.bins.base, N * kNumBins * sizeof(uint32_t)));
   m.bins.stride = static_cast<uint32_t>(N);
   RT2_CUDA(cudaMalloc(&m.counters, static_cast<size_t>(cfg_.max_depth + 1) * kCounterStride * sizeof(uint32_t)));
@@ -535,7 +578,7 @@ int Renderer::Reset() {
   const size_t P = static_cast<size_t>(width_) * height_;
   RT2_CUDA(cudaMemsetAsync(m.accum, 0, P * sizeof(float4), m.stream));
   if (m.accum_sq) RT2_CUDA(cudaMemsetAsync(m.accum_sq, 0, P * sizeof(float4), m.stream));
-  RT2_CUDA(cudaMemsetAsync(m.totals, 0, 4 * sizeof(unsigned long long), m.stream));
+  RT2_CUDA(cudaMemsetAsync(m.totals, 0, 8 * sizeof(unsigned long long), m.stream));
   frame_idx_ = 0;
   gpu_ms_total_ = 0;
   for (double& v : prof_ms_) v = 0;
@@ -597,14 +640,23 @@ int Renderer::RenderBatch(uint32_t n_frames) {
     uint32_t* next = m.counters + static_cast<size_t>(b + 1) * kCounterStride;
     const int out = in ^ 1;
     prof(1);
+    unsigned long long* work = m.totals + 2;
     if (exact) {
-      k_extend<ExactMath><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.hit0,
-                                                                  m.hit1, m.bins);
+      if (profiling_) k_traverse<ExactMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], m.trav, work);
+      else k_traverse<ExactMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], m.trav, work);
     } else {
-      k_extend<FastMath><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.hit0,
-                                                                 m.hit1, m.bins);
+      if (profiling_) k_traverse<FastMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], m.trav, work);
+      else k_traverse<FastMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], m.trav, work);
     }
-    launches_++;
+    prof(3);
+    if (exact) {
+      k_finish_hit<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, m.hit0,
+                                                                      m.hit1, m.bins);
+    } else {
+      k_finish_hit<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, m.hit0,
+                                                                     m.hit1, m.bins);
+    }
+    launches_ += 2;
     prof(2);
     const bool last = (b + 1 == max_depth);  // RayColor(depth <= 0) returns black: nothing to scatter into
     k_shade_terminal<<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, last ? nullptr : next, m.bins.q(0), m.state[in], m.hit0, m.hit1,
@@ -623,7 +675,7 @@ int Renderer::RenderBatch(uint32_t n_frames) {
   k_accumulate<<<m.grid_stream, kBlock, 0, m.stream>>>(P, n_frames, m.radiance, m.accum, m.accum_sq);
   k_batch_stats<<<1, 32, 0, m.stream>>>(m.counters, max_depth, m.totals);
   launches_ += 2;
-  prof(3);
+  prof(4);
   RT2_CUDA(cudaGetLastError());
   if (profiling_) {
     RT2_CUDA(cudaStreamSynchronize(m.stream));
@@ -631,7 +683,7 @@ int Renderer::RenderBatch(uint32_t n_frames) {
       float ms = 0;
       cudaEventElapsedTime(&ms, m.prof_events[i], m.prof_events[i + 1]);
       int kind = m.prof_kind[i];
-      if (kind >= 0 && kind < 3) prof_ms_[kind] += ms;
+      if (kind >= 0 && kind < 4) prof_ms_[kind] += ms;
     }
   }
   return RT2_OK;
@@ -640,7 +692,17 @@ int Renderer::RenderBatch(uint32_t n_frames) {
 int Renderer::Update(uint32_t n_frames) {
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
-  RT2_CUDA(cudaEventRecord(m.ev_start, m.stream));
+  // one CUDA-event pair per call; folded into gpu_ms_total at the next synchronisation
+  if (m.timing_used + 2 > m.timing_events.size()) {
+    for (int k = 0; k < 2; k++) {
+      cudaEvent_t e;
+      RT2_CUDA(cudaEventCreate(&e));
+      m.timing_events.push_back(e);
+    }
+  }
+  cudaEvent_t ev_a = m.timing_events[m.timing_used], ev_b = m.timing_events[m.timing_used + 1];
+  m.timing_used += 2;
+  RT2_CUDA(cudaEventRecord(ev_a, m.stream));
   while (n_frames > 0) {
     uint32_t f = n_frames < static_cast<uint32_t>(frames_per_batch_) ? n_frames : static_cast<uint32_t>(frames_per_batch_);
     int rc = RenderBatch(f);
@@ -648,7 +710,7 @@ int Renderer::Update(uint32_t n_frames) {
     frame_idx_ += f;
     n_frames -= f;
   }
-  RT2_CUDA(cudaEventRecord(m.ev_stop, m.stream));
+  RT2_CUDA(cudaEventRecord(ev_b, m.stream));
   timing_pending_ = true;
   return RT2_OK;
 }
@@ -658,8 +720,11 @@ int Renderer::Synchronize() {
   RT2_CUDA(cudaSetDevice(cfg_.device));
   RT2_CUDA(cudaStreamSynchronize(m.stream));
   if (timing_pending_) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, m.ev_start, m.ev_stop) == cudaSuccess) gpu_ms_total_ += ms;
+    for (size_t i = 0; i + 1 < m.timing_used; i += 2) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, m.timing_events[i], m.timing_events[i + 1]) == cudaSuccess) gpu_ms_total_ += ms;
+    }
+    m.timing_used = 0;
     timing_pending_ = false;
   }
   return RT2_OK;
@@ -733,31 +798,52 @@ int Renderer::Intersect(const float* rays, size_t n, float tmin, float tmax, int
     err_ = "too many rays";
     return RT2_ERR_INVALID_ARG;
   }
-  float4* d_rays = nullptr;
+  // split the interleaved input (origin xyz, time | direction xyz, pad) into the two arrays the traversal reads
+  std::vector<float4> h_o(n), h_d(n);
+  for (size_t i = 0; i < n; i++) {
+    h_o[i] = make_float4(rays[8 * i + 0], rays[8 * i + 1], rays[8 * i + 2], rays[8 * i + 3]);
+    h_d[i] = make_float4(rays[8 * i + 4], rays[8 * i + 5], rays[8 * i + 6], 0.0f);
+  }
+  float4* d_o = nullptr;
+  float4* d_d = nullptr;
+  uint4* d_trav = nullptr;
+  uint32_t* d_cursor = nullptr;
   rt2_hit* d_out = nullptr;
-  RT2_CUDA(cudaMalloc(&d_rays, n * 2 * sizeof(float4)));
-  cudaError_t e = cudaMalloc(&d_out, n * sizeof(rt2_hit));
-  if (e != cudaSuccess) {
-    cudaFree(d_rays);
+  auto cleanup = [&]() {
+    if (d_o) cudaFree(d_o);
+    if (d_d) cudaFree(d_d);
+    if (d_trav) cudaFree(d_trav);
+    if (d_cursor) cudaFree(d_cursor);
+    if (d_out) cudaFree(d_out);
+  };
+  cudaError_t e = cudaSuccess;
+  if ((e = cudaMalloc(&d_o, n * sizeof(float4))) != cudaSuccess || (e = cudaMalloc(&d_d, n * sizeof(float4))) != cudaSuccess ||
+      (e = cudaMalloc(&d_trav, n * sizeof(uint4))) != cudaSuccess || (e = cudaMalloc(&d_cursor, sizeof(uint32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&d_out, n * sizeof(rt2_hit))) != cudaSuccess) {
+    cleanup();
     err_ = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
     return RT2_ERR_CUDA;
   }
-  cudaMemcpyAsync(d_rays, rays, n * 2 * sizeof(float4), cudaMemcpyHostToDevice, m.stream);
-  const uint32_t grid = static_cast<uint32_t>((n + kBlock - 1) / kBlock);
+  cudaMemcpyAsync(d_o, h_o.data(), n * sizeof(float4), cudaMemcpyHostToDevice, m.stream);
+  cudaMemcpyAsync(d_d, h_d.data(), n * sizeof(float4), cudaMemcpyHostToDevice, m.stream);
+  cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t), m.stream);
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  const uint32_t grid = (n32 + kBlock - 1) / kBlock;
+  const uint32_t tgrid = grid < static_cast<uint32_t>(m.grid_extend) ? grid : static_cast<uint32_t>(m.grid_extend);
+  const uint32_t seed_lo = static_cast<uint32_t>(cfg_.seed), seed_hi = static_cast<uint32_t>(cfg_.seed >> 32);
   if (cfg_.flags & RT2_FLAG_FAST_MATH) {
-    k_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_rays, static_cast<uint32_t>(n), tmin, tmax, skip_media,
-                                                         static_cast<uint32_t>(cfg_.seed), static_cast<uint32_t>(cfg_.seed >> 32), d_out);
+    k_traverse_rays<FastMath><<<tgrid, kBlock, 0, m.stream>>>(m.ds, n32, d_cursor, d_o, d_d, tmin, tmax, d_trav);
+    k_finish_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
   } else {
-    k_intersect<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_rays, static_cast<uint32_t>(n), tmin, tmax, skip_media,
-                                                          static_cast<uint32_t>(cfg_.seed), static_cast<uint32_t>(cfg_.seed >> 32), d_out);
+    k_traverse_rays<ExactMath><<<tgrid, kBlock, 0, m.stream>>>(m.ds, n32, d_cursor, d_o, d_d, tmin, tmax, d_trav);
+    k_finish_intersect<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
   }
-  launches_++;
+  launches_ += 2;
   cudaMemcpyAsync(out, d_out, n * sizeof(rt2_hit), cudaMemcpyDeviceToHost, m.stream);
   e = cudaStreamSynchronize(m.stream);
-  cudaFree(d_rays);
-  cudaFree(d_out);
+  cleanup();
   if (e != cudaSuccess) {
-    err_ = std::string("k_intersect failed: ") + cudaGetErrorString(e);
+    err_ = std::string("rt2_intersect kernels failed: ") + cudaGetErrorString(e);
     return RT2_ERR_CUDA;
   }
   return RT2_OK;
@@ -767,7 +853,7 @@ int Renderer::GetStats(rt2_stats* out) {
   Impl& m = *impl_;
   int rc = Synchronize();
   if (rc != RT2_OK) return rc;
-  unsigned long long t[4];
+  unsigned long long t[8];
   RT2_CUDA(cudaMemcpy(t, m.totals, sizeof(t), cudaMemcpyDeviceToHost));
   out->rays = t[0];
   out->paths = t[1];
@@ -777,6 +863,11 @@ int Renderer::GetStats(rt2_stats* out) {
   out->gpu_ms_other = prof_ms_[0];
   out->gpu_ms_extend = prof_ms_[1];
   out->gpu_ms_shade = prof_ms_[2];
+  out->gpu_ms_finish = prof_ms_[3];
+  out->box_pair_tests = t[2];
+  out->sphere_tests = t[3];
+  out->quad_tests = t[4];
+  out->instance_visits = t[5];
   return RT2_OK;
 }
 

@@ -160,126 +160,186 @@ __device__ __forceinline__ bool list_hit(const DeviceScene& S, uint32_t first, u
   return any;
 }
 
-// Surface traversal: two-level BVH (world TLAS whose instance leaves enter a per-instance BLAS), one loop, explicit
-// stack.  Box tests only cull; they are made conservative (see cull_scale) so the result is the exact arg-min.
-template <class M>
-__device__ __forceinline__ void trace_surfaces(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, float tmax,
-                                               Closest& best) {
+// Per-lane traversal counters (profiling build of k_traverse): algorithmic work actually done by ACTIVE lanes.
+struct TravCounters {
+  uint32_t box_pairs{0}, spheres{0}, quads{0}, instances{0};
+};
+
+// Surface traversal of a whole ray queue by persistent warps (one lane = one ray at a time).
+//
+// Two-level BVH: world TLAS whose (singleton) instance leaves switch the lane to the instance's model space and BLAS;
+// a sentinel on the stack switches back.  Box tests only cull and are conservative (see cull_scale), so the result is
+// the exact arg-min over leaves of the raw reported t.
+//
+// SIMT shape ("while-while" with dynamic fetch, after Aila & Laine 2009): the warp alternates between
+//   phase 1  every lane descends interior nodes until it holds a leaf (or its ray is finished),
+//   phase 2  every lane that holds a leaf intersects its primitives,
+// reconverging with __syncwarp() between the phases, so the expensive exact-arithmetic primitive tests run with many
+// lanes instead of whichever lanes happen to reach a leaf in the same iteration.  Lanes whose ray is finished write
+// the result and idle; when fewer than kFetchThreshold lanes are busy the warp pulls new rays from the queue with one
+// atomic.  Results go to trav_out[ray] = {t bits, prim ref, instance, 0}.
+template <class M, bool kCount, int kFetchThreshold>
+__device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n, const float4* __restrict__ ray_o,
+                                               const float4* __restrict__ ray_d, float tmin, float tmax,
+                                               uint32_t* __restrict__ next_ray, uint4* __restrict__ trav_out,
+                                               TravCounters& cnt) {
+  const unsigned kFull = 0xFFFFFFFFu;
+  const unsigned lane = threadIdx.x & 31u;
   uint32_t stack[kStackSize];
   int sp = 0;
-  best.t = tmax;
-  best.prim = RT2_PRIM_NONE;
-  best.instance = -1;
-
-  F3 o = wo, d = wd;
-  float a = vdot<M>(d, d);
-  // An instanced leaf reports t in model units (= world t * |M^-1 d|), so a world-space box at parameter t_w can hold
-  // an instanced hit with raw t as small as t_w * sigma_min * |d|: scale the culling bound accordingly.
-  float cull_scale = 1.0f;
-  if (S.n_instances > 0) cull_scale = fmaxf(1.0f, 1.0f / (S.min_inv_scale * sqrtf(a)));
-  float cur_cull = cull_scale;
+  bool active = false;
+  bool exhausted = false;
+  uint32_t ray_idx = 0;
+  uint32_t cur = 0;
+  F3 o = {0, 0, 0}, d = {0, 0, 1};
+  float time = 0.0f, a = 1.0f;
+  F3 inv = {0, 0, 0}, oid = {0, 0, 0};
+  float cull_scale = 1.0f, cur_cull = 1.0f;
   int32_t cur_inst = -1;
-  F3 inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
-  F3 oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
+  Closest best{tmax, RT2_PRIM_NONE, -1};
 
-  uint32_t cur = S.tlas_root;  // interior entry = node-pair index
-  while (true) {
-    if (!(cur & kLeafFlag)) {
-      const float4* np = S.nodes + static_cast<size_t>(cur) * 4;
-      const float4 a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
-      const float bound = best.t * cur_cull;
-      // child 0
-      float t0x = fmaf(a0.x, inv.x, oid.x), t1x = fmaf(a1.x, inv.x, oid.x);
-      float t0y = fmaf(a0.y, inv.y, oid.y), t1y = fmaf(a1.y, inv.y, oid.y);
-      float t0z = fmaf(a0.z, inv.z, oid.z), t1z = fmaf(a1.z, inv.z, oid.z);
-      float near0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-      float far0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-      bool h0 = (near0 * 0.9999995f <= far0 * 1.0000005f) && (near0 * 0.9999995f <= bound);
-      // child 1
-      t0x = fmaf(b0.x, inv.x, oid.x), t1x = fmaf(b1.x, inv.x, oid.x);
-      t0y = fmaf(b0.y, inv.y, oid.y), t1y = fmaf(b1.y, inv.y, oid.y);
-      t0z = fmaf(b0.z, inv.z, oid.z), t1z = fmaf(b1.z, inv.z, oid.z);
-      float near1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-      float far1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-      bool h1 = (near1 * 0.9999995f <= far1 * 1.0000005f) && (near1 * 0.9999995f <= bound);
-
-      const uint32_t c0 = __float_as_uint(a1.w), c1 = __float_as_uint(b1.w);
-      // entry: interior -> child pair index; leaf -> flag | (count-1) << 27 | first
-      uint32_t e0 = c0 ? (kLeafFlag | ((c0 - 1u) << 27) | __float_as_uint(a0.w)) : __float_as_uint(a0.w);
-      uint32_t e1 = c1 ? (kLeafFlag | ((c1 - 1u) << 27) | __float_as_uint(b0.w)) : __float_as_uint(b0.w);
-      if (h0 && h1) {
-        bool swap = near1 < near0;
-        cur = swap ? e1 : e0;
-        RT2_STACK_GUARD stack[sp++] = swap ? e0 : e1;  // the host builder bounds the depth; never write past the stack
-        continue;
-      }
-      if (h0) {
-        cur = e0;
-        continue;
-      }
-      if (h1) {
-        cur = e1;
-        continue;
-      }
-    } else {
-      const uint32_t first = cur & 0x07FFFFFFu;
-      const uint32_t count = ((cur >> 27) & 0xFu) + 1u;
-      bool entered = false;
-      for (uint32_t i = 0; i < count; i++) {
-        const uint32_t ref = __ldg(S.prim_refs + first + i);
-        const uint32_t type = RT2_PRIM_TYPE(ref), idx = RT2_PRIM_INDEX(ref);
-        if (type == RT2_PRIM_SPHERE) {
-          float t;
-          if (sphere_hit<M>(__ldg(S.spheres + 2 * idx), __ldg(S.spheres + 2 * idx + 1), o, d, a, time, tmin, best.t, t)) {
-            best.t = t;
-            best.prim = ref;
-            best.instance = cur_inst;
-          }
-        } else if (type == RT2_PRIM_QUAD) {
-          float t;
-          if (quad_hit<M>(S.quads + 5 * idx, o, d, tmin, best.t, t)) {
-            best.t = t;
-            best.prim = ref;
-            best.instance = cur_inst;
-          }
-        } else {
-          // instance leaf (always a singleton leaf of the TLAS): enter its BLAS in model space
-          const uint4 in = __ldg(S.instances + idx);
-          RaySpace ms = to_chain_space<M>(S, in.x, in.y, RaySpace{wo, wd});
-          o = ms.o;
-          d = ms.d;
-          a = vdot<M>(d, d);
-          inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
-          oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
-          cur_inst = static_cast<int32_t>(idx);
-          cur_cull = 1.0f;
-          RT2_STACK_GUARD stack[sp++] = kStackSentinel;
-          cur = in.z;
-          entered = true;
-          break;  // instance references are singleton leaves (host/bvh_build.cpp)
-        }
-      }
-      if (entered) continue;
-    }
-    // pop
-    bool done = false;
+  auto set_space = [&](F3 no, F3 nd) {
+    o = no;
+    d = nd;
+    a = vdot<M>(d, d);
+    inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
+    oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
+  };
+  // Pops the next entry; on an empty stack the ray is finished: publish the result and free the lane.
+  auto pop = [&]() {
     while (true) {
       if (sp == 0) {
-        done = true;
-        break;
+        trav_out[ray_idx] = make_uint4(__float_as_uint(best.t), best.prim, static_cast<uint32_t>(best.instance), 0u);
+        active = false;
+        return;
       }
       cur = stack[--sp];
-      if (cur != kStackSentinel) break;
-      // leave the instance: back to the world-space ray
-      o = wo;
-      d = wd;
-      a = vdot<M>(d, d);
-      inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
-      oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
+      if (cur != kStackSentinel) return;
+      // leave the instance: back to the world-space ray (re-read instead of holding it in registers)
+      const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
+      set_space(make_f3(wo), make_f3(wd));
       cur_inst = -1;
       cur_cull = cull_scale;
     }
-    if (done) break;
+  };
+
+  while (true) {
+    // ---- fetch: idle lanes take the next rays of the queue (one atomic per warp) ----
+    const unsigned idle = __ballot_sync(kFull, !active);
+    if (idle) {
+      if (!exhausted) {
+        const int leader = __ffs(idle) - 1;
+        uint32_t base = 0;
+        if (static_cast<int>(lane) == leader) base = atomicAdd(next_ray, __popc(idle));
+        base = __shfl_sync(kFull, base, leader);
+        if (!active) {
+          const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+          if (idx < n) {
+            ray_idx = idx;
+            const float4 wo = ray_o[idx], wd = ray_d[idx];
+            time = wo.w;
+            set_space(make_f3(wo), make_f3(wd));
+            // An instanced leaf reports t in model units (= world t * |M^-1 d|): a world-space box at parameter t_w can
+            // hold an instanced hit with raw t as small as t_w * sigma_min * |d|, so scale the TLAS culling bound.
+            cull_scale = (S.n_instances > 0) ? fmaxf(1.0f, 1.0f / (S.min_inv_scale * sqrtf(a))) : 1.0f;
+            cur_cull = cull_scale;
+            cur_inst = -1;
+            best.t = tmax;
+            best.prim = RT2_PRIM_NONE;
+            best.instance = -1;
+            sp = 0;
+            cur = S.tlas_root;
+            active = true;
+          }
+        }
+        exhausted = (base + __popc(idle)) >= n;
+      }
+      if (__ballot_sync(kFull, active) == 0u) break;
+    }
+
+    // ---- traverse until too few lanes are busy ----
+    while (true) {
+      // phase 1: interior nodes
+      while (active && !(cur & kLeafFlag)) {
+        const float4* np = S.nodes + static_cast<size_t>(cur) * 4;
+        const float4 a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
+        if (kCount) cnt.box_pairs++;
+        const float bound = best.t * cur_cull;
+        float t0x = fmaf(a0.x, inv.x, oid.x), t1x = fmaf(a1.x, inv.x, oid.x);
+        float t0y = fmaf(a0.y, inv.y, oid.y), t1y = fmaf(a1.y, inv.y, oid.y);
+        float t0z = fmaf(a0.z, inv.z, oid.z), t1z = fmaf(a1.z, inv.z, oid.z);
+        const float near0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+        const float far0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+        const bool h0 = (near0 * 0.9999995f <= far0 * 1.0000005f) && (near0 * 0.9999995f <= bound);
+        t0x = fmaf(b0.x, inv.x, oid.x), t1x = fmaf(b1.x, inv.x, oid.x);
+        t0y = fmaf(b0.y, inv.y, oid.y), t1y = fmaf(b1.y, inv.y, oid.y);
+        t0z = fmaf(b0.z, inv.z, oid.z), t1z = fmaf(b1.z, inv.z, oid.z);
+        const float near1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+        const float far1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+        const bool h1 = (near1 * 0.9999995f <= far1 * 1.0000005f) && (near1 * 0.9999995f <= bound);
+        const uint32_t c0 = __float_as_uint(a1.w), c1 = __float_as_uint(b1.w);
+        // entry: interior -> child pair index; leaf -> flag | (count-1) << 27 | first
+        const uint32_t e0 = c0 ? (kLeafFlag | ((c0 - 1u) << 27) | __float_as_uint(a0.w)) : __float_as_uint(a0.w);
+        const uint32_t e1 = c1 ? (kLeafFlag | ((c1 - 1u) << 27) | __float_as_uint(b0.w)) : __float_as_uint(b0.w);
+        if (h0 && h1) {
+          const bool swap = near1 < near0;
+          cur = swap ? e1 : e0;
+          RT2_STACK_GUARD stack[sp++] = swap ? e0 : e1;  // the host builder bounds the depth; never write past the stack
+        } else if (h0) {
+          cur = e0;
+        } else if (h1) {
+          cur = e1;
+        } else {
+          pop();
+        }
+      }
+      __syncwarp();
+      // phase 2: leaves
+      if (active) {
+        const uint32_t first = cur & 0x07FFFFFFu;
+        const uint32_t count = ((cur >> 27) & 0xFu) + 1u;
+        bool entered = false;
+        for (uint32_t i = 0; i < count; i++) {
+          const uint32_t ref = __ldg(S.prim_refs + first + i);
+          const uint32_t type = RT2_PRIM_TYPE(ref), idx = RT2_PRIM_INDEX(ref);
+          if (type == RT2_PRIM_SPHERE) {
+            if (kCount) cnt.spheres++;
+            float t;
+            if (sphere_hit<M>(__ldg(S.spheres + 2 * idx), __ldg(S.spheres + 2 * idx + 1), o, d, a, time, tmin, best.t, t)) {
+              best.t = t;
+              best.prim = ref;
+              best.instance = cur_inst;
+            }
+          } else if (type == RT2_PRIM_QUAD) {
+            if (kCount) cnt.quads++;
+            float t;
+            if (quad_hit<M>(S.quads + 5 * idx, o, d, tmin, best.t, t)) {
+              best.t = t;
+              best.prim = ref;
+              best.instance = cur_inst;
+            }
+          } else {
+            // instance leaf (always a singleton leaf of the TLAS, host/bvh_build.cpp): enter its BLAS in model space
+            if (kCount) cnt.instances++;
+            const uint4 in = __ldg(S.instances + idx);
+            const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
+            RaySpace ms = to_chain_space<M>(S, in.x, in.y, RaySpace{make_f3(wo), make_f3(wd)});
+            set_space(ms.o, ms.d);
+            cur_inst = static_cast<int32_t>(idx);
+            cur_cull = 1.0f;
+            RT2_STACK_GUARD stack[sp++] = kStackSentinel;
+            cur = in.z;
+            entered = true;
+            break;
+          }
+        }
+        if (!entered) pop();
+      }
+      __syncwarp();
+      const unsigned busy = __ballot_sync(kFull, active);
+      if (busy == 0u) break;
+      if (!exhausted && __popc(busy) < kFetchThreshold) break;
+    }
   }
 }
 
@@ -317,12 +377,11 @@ struct HitOut {
   int32_t instance;
 };
 
-// Full closest-hit query ≡ scene.hittable_list.Hit(r, Interval{tmin, tmax}, rec) (RayTracer.cpp:25).
+// Second half of the closest-hit query ≡ scene.hittable_list.Hit(r, Interval{tmin, tmax}, rec) (RayTracer.cpp:25):
+// given the closest SURFACE (traverse_queue), sample the constant media against it and build the winner's record.
 template <class M>
-__device__ __forceinline__ void closest_hit(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, float tmax,
-                                            const RngKey& key, uint32_t bounce, bool skip_media, HitOut& out) {
-  Closest best;
-  trace_surfaces<M>(S, wo, wd, time, tmin, tmax, best);
+__device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, Closest best,
+                                           const RngKey& key, uint32_t bounce, bool skip_media, HitOut& out) {
 
   // constant media (few per scene): each draws its free path against the current best raw t
   int32_t medium_hit = -1;

@@ -15,7 +15,7 @@ def run(name, spp_total, spp, fpb, flags=0, dims=None, reps=3, label=""):
     st = tr.stats()
     tr.Reset(); tr.set_profiling(True); tr.Update(spp); ps = tr.stats()
     print(f"{label or name}: spp_total={spp_total} spp={spp} fpb={fpb} flags={flags} dims={tr.Dims()} -> {st['rays']/st['gpu_ms_total']*1e-3:.1f} Mrays/s "
-          f"({st['gpu_ms_total']/reps:.2f} ms per {spp} spp, rays/path {st['rays']/st['paths']:.3f}) | profiled split ms: extend {ps['gpu_ms_extend']:.2f} shade {ps['gpu_ms_shade']:.2f} other {ps['gpu_ms_other']:.2f}", flush=True)
+          f"({st['gpu_ms_total']/reps:.2f} ms per {spp} spp, rays/path {st['rays']/st['paths']:.3f}) | profiled split ms: traverse {ps['gpu_ms_extend']:.2f} finish {ps['gpu_ms_finish']:.2f} shade {ps['gpu_ms_shade']:.2f} other {ps['gpu_ms_other']:.2f} | per ray: box-pairs {ps['box_pair_tests']/ps['rays']:.1f} spheres {ps['sphere_tests']/ps['rays']:.1f} quads {ps['quad_tests']/ps['rays']:.1f} inst {ps['instance_visits']/ps['rays']:.2f}", flush=True)
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "book2"
