@@ -38,11 +38,11 @@ EXTEND_BYTES_PER_RAY = 16 + 16 + 16
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scene", default=DEFAULT_SCENE, help="scene name under data/ (or 'synthetic:<n_spheres>')")
-    ap.add_argument("--spp-per-step", type=int, default=16)
+    ap.add_argument("--spp-per-step", type=int, default=64)
     ap.add_argument("--spp-total", type=int, default=10000, help="samples-per-pixel setting (fixes the stratification grid)")
     ap.add_argument("--max-depth", type=int, default=50)
     ap.add_argument("--width", type=int, default=0)

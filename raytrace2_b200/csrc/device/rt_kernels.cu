@@ -543,9 +543,10 @@ int Renderer::Resize(int w, int h) {
   const size_t P = static_cast<size_t>(w) * h;
   int F = cfg_.frames_per_batch;
   if (F <= 0) {
-    F = static_cast<int>((6u * 1024u * 1024u + P - 1) / P);  // ~6M paths in flight
+    // ~24M paths in flight (~4 GB of wavefront state): amortises the ~8 launches per bounce over big queues
+    F = static_cast<int>((24u * 1024u * 1024u + P - 1) / P);
     if (F < 1) F = 1;
-    if (F > 64) F = 64;
+    if (F > 256) F = 256;
   }
   frames_per_batch_ = F;
   const size_t N = P * static_cast<size_t>(F);

@@ -343,27 +343,29 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
   }
 }
 
-// ConstantMedium::Hit (ConstantMedium.cpp:14-58) for medium m against the current best t.  `xi` is the uniform draw.
+// ConstantMedium::Hit (ConstantMedium.cpp:14-58), split in two: the boundary queries (deterministic, independent of the
+// caller's interval) and the free-path draw against the current [tmin, tmax].  A medium in a span-1 leaf of the
+// reference BVH has Hit() called twice (quirk Q2): both calls see identical boundary records, so they are computed once.
 template <class M>
-__device__ __forceinline__ bool medium_sample(const DeviceScene& S, const uint4 m0, const uint4 m1, F3 o, F3 d, float time,
-                                              float tmin, float tmax, float xi, float& t_out) {
-  const float a = vdot<M>(d, d);
-  float t1, t2;
+__device__ __forceinline__ bool medium_boundary(const DeviceScene& S, const uint4 m0, F3 o, F3 d, float a, float time, float& t1,
+                                                float& t2) {
   // boundary_->Hit(r, Interval::kUniverse, rec1)
   if (!list_hit<M>(S, m0.z, m0.w, o, d, a, time, -kFltMax, kFltMax, t1)) return false;
   // boundary_->Hit(r, Interval(rec1.t + 0.0001, kInfinity), rec2): the sum is formed in double, then stored as float
   const float t1_eps = static_cast<float>(static_cast<double>(t1) + 0.0001);
-  if (!list_hit<M>(S, m0.z, m0.w, o, d, a, time, t1_eps, kFltMax, t2)) return false;
+  return list_hit<M>(S, m0.z, m0.w, o, d, a, time, t1_eps, kFltMax, t2);
+}
+template <class M>
+__device__ __forceinline__ bool medium_draw(float neg_inv_density, float ray_len, float t1, float t2, float tmin, float tmax, float xi,
+                                            float& t_out) {
   t1 = fmaxf(t1, tmin);
   t2 = fminf(t2, tmax);
   if (t1 >= t2) return false;
   t1 = fmaxf(t1, 0.0f);
-  const float ray_len = M::sqrt(a);  // glm::length
   const float dist_inside = M::mul(M::sub(t2, t1), ray_len);
-  const float hit_dist = M::mul(__uint_as_float(m0.x), logf(xi));
+  const float hit_dist = M::mul(neg_inv_density, logf(xi));
   if (hit_dist > dist_inside) return false;
   t_out = M::add(t1, M::div(hit_dist, ray_len));
-  (void)m1;
   return true;
 }
 
@@ -389,14 +391,18 @@ __device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, f
     for (uint32_t m = 0; m < S.n_media; m++) {
       const uint4 m0 = __ldg(S.media + 2 * m), m1 = __ldg(S.media + 2 * m + 1);
       RaySpace rs = to_chain_space<M>(S, m1.x, m1.y, RaySpace{wo, wd});
+      const float a = vdot<M>(rs.d, rs.d);
+      float t1, t2;
+      if (!medium_boundary<M>(S, m0, rs.o, rs.d, a, time, t1, t2)) continue;
+      const float ray_len = M::sqrt(a);  // glm::length(r.direction)
       const uint4 r = rng_draw(key, bounce, kStreamMedium + m);
       float t;
-      if (medium_sample<M>(S, m0, m1, rs.o, rs.d, time, tmin, best.t, u01(r.x), t)) {
+      if (medium_draw<M>(__uint_as_float(m0.x), ray_len, t1, t2, tmin, best.t, u01(r.x), t)) {
         best.t = t;
         medium_hit = static_cast<int32_t>(m);
       }
       if (m1.z) {  // span-1 leaf of the reference BVH: Hit() runs twice, the second against the shrunken interval
-        if (medium_sample<M>(S, m0, m1, rs.o, rs.d, time, tmin, best.t, u01(r.y), t)) {
+        if (medium_draw<M>(__uint_as_float(m0.x), ray_len, t1, t2, tmin, best.t, u01(r.y), t)) {
           best.t = t;
           medium_hit = static_cast<int32_t>(m);
         }
