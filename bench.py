@@ -301,7 +301,7 @@ def run_ours(args):
         "config": {"workload": f"{scene_label} {W}x{H}, max_depth {args.max_depth}, {S} spp per step per GPU",
                    "spp_per_step_per_gpu": S, "paths_per_s": paths_all / (ms_all * 1e-3), "rays_per_path": rays_all / max(paths_all, 1),
                    "intersection_math": "fast (FMA)" if args.fast_math else "exact (bit-identical with the reference)",
-                   "l2": "wavefront state per step (%.0f MB) exceeds L2; no explicit flush" % (W * H * S * 168 / 1e6),
+                   "l2": "wavefront state per step (%.0f MB) exceeds L2; no explicit flush" % (W * H * S * 184 / 1e6),
                    "parallelism": f"sample-partition x{world}" if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "roofline": roofline,
     }

@@ -192,3 +192,34 @@ def test_run_app_headless(native_lib, tmp_path):
     rc = rt.run_app(["raytrace_2", scene_path("cornell_original_test")[:-5], str(out)], str(settings), os.path.dirname(scene_path("x")))
     assert rc == 0 and out.exists() and out.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
     assert rt.run_app(["raytrace_2", "/nonexistent_scene", str(out)], str(settings), None) != 0
+
+
+def test_cpp_adapter_example(native_lib, tmp_path):
+    """include/rt2_raytracer.hpp (the adapter with the reference's method names) + examples/headless_app.cpp = the headless
+    branch of App::Run as a maintainer would write it after the swap (INTEGRATION.md §2)."""
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "headless_app"
+    lib_dir = os.path.join(ROOT, "raytrace2_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "headless_app.cpp"),
+                           "-L" + lib_dir, "-lraytrace2_b200", "-Wl,-rpath," + lib_dir, "-o", str(exe)])
+    out = tmp_path / "cornell.png"
+    subprocess.check_call([str(exe), scene_path("cornell_original_test"), str(out), "16"])
+    data = out.read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n" and len(data) > 10000
+
+
+def test_cli_binary(native_lib, tmp_path):
+    """raytrace2_b200/bin/raytrace_2 <scene-without-.json> <out.png> with $RAYTRACE2_ROOT/local/data/settings.json."""
+    import subprocess
+    from conftest import ROOT
+    root = tmp_path / "root"
+    (root / "local" / "data").mkdir(parents=True)
+    (root / "local" / "data" / "settings.json").write_text(json.dumps({"num_samples": 4, "max_depth": 50, "render_window": False}))
+    os.symlink(os.path.join(ROOT, "data"), root / "data")
+    out = tmp_path / "o.png"
+    env = dict(os.environ, RAYTRACE2_ROOT=str(root))
+    exe = os.path.join(ROOT, "raytrace2_b200", "bin", "raytrace_2")
+    res = subprocess.run([exe, scene_path("cornell_volume_10000_samples")[:-5], str(out)], env=env, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert "Num Samples: 4" in res.stdout and "Writing image:" in res.stdout and out.exists()
