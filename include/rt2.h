@@ -178,8 +178,11 @@ typedef struct rt2_scene rt2_scene;
  * perlin_seed: seeds the host generator of the random Perlin tables (the reference seeds from random_device). */
 int rt2_scene_load(const char* json_path, const char* data_dir, uint64_t perlin_seed, rt2_scene** out);
 int rt2_scene_load_string(const char* json_text, const char* data_dir, uint64_t perlin_seed, rt2_scene** out);
-/* Synthetic BVH stress scene: n random spheres + ground sphere, book-1 material recipe. */
-int rt2_scene_synthetic_spheres(uint32_t n_spheres, uint64_t seed, int32_t width, int32_t height, rt2_scene** out);
+/* Synthetic BVH stress scene: n random spheres + ground sphere, book-1 material recipe.
+ * build_host_bvh = 0 skips the host SAH build (seconds per million spheres); such a scene can only be rendered with
+ * RT2_FLAG_GPU_LBVH. */
+int rt2_scene_synthetic_spheres(uint32_t n_spheres, uint64_t seed, int32_t width, int32_t height, int32_t build_host_bvh,
+                                rt2_scene** out);
 void rt2_scene_destroy(rt2_scene* scene);
 /* Borrowed pointers into the scene, valid until the scene is modified or destroyed. */
 int rt2_scene_get_desc(const rt2_scene* scene, rt2_scene_desc* out);
@@ -199,7 +202,9 @@ typedef struct rt2_renderer rt2_renderer;
 
 #define RT2_FLAG_MOMENTS 1u     /* also accumulate per-pixel sum of squares (z-score parity test) */
 #define RT2_FLAG_FAST_MATH 2u   /* FMA-contracted intersection arithmetic (default: bit-exact with the reference) */
-#define RT2_FLAG_NO_BINNING 4u  /* one fused shade kernel instead of per-material queues (ablation) */
+#define RT2_FLAG_NO_BINNING 4u  /* reserved */
+#define RT2_FLAG_GPU_LBVH 8u    /* build every BVH on the device (Morton codes + radix sort + Karras hierarchy) instead of
+                                   uploading the host SAH trees */
 
 typedef struct rt2_config {
   int32_t device;            /* CUDA device ordinal */
@@ -223,6 +228,7 @@ typedef struct rt2_stats {
   double gpu_ms_shade;  /* ... of the shade kernels */
   double gpu_ms_other;  /* ... of generate / accumulate / stats */
   double gpu_ms_finish; /* ... of k_finish_hit (media + hit record + binning) */
+  double gpu_ms_bvh_build; /* CUDA-event time of the last device-side LBVH build (RT2_FLAG_GPU_LBVH), else 0 */
   /* algorithmic work done by active lanes of k_traverse while profiling is enabled */
   uint64_t box_pair_tests; /* node-pair visits = 2 AABB slab tests each */
   uint64_t sphere_tests;
@@ -270,6 +276,10 @@ int rt2_set_frame_idx(rt2_renderer* r, uint64_t frames);
 /* Fixed-ray parity hook ≡ scene.hittable_list.Hit(ray, Interval{tmin,tmax}) (RayTracer.cpp:25). rays: n x 8 floats
  * (origin xyz, time, direction xyz, pad). Media are sampled with Philox keyed on the ray index unless skip_media != 0. */
 int rt2_intersect(rt2_renderer* r, const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out);
+/* Copies the BVH the device traverses back to the host (inspection / tests): nodes = 2 * n_pairs entries. Pass NULL
+ * buffers to query the sizes only. */
+int rt2_read_bvh(rt2_renderer* r, rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs, size_t max_refs, uint32_t* n_pairs,
+                 uint32_t* n_refs, uint32_t* tlas_root);
 int rt2_get_stats(rt2_renderer* r, rt2_stats* out);
 int rt2_set_profiling(rt2_renderer* r, int enabled); /* per-kernel CUDA-event timing (serialises launches) */
 /* CUDA stream the renderer launches on (cudaStream_t as void*), for external event timing. */

@@ -22,6 +22,7 @@ RT2_ERR_STATE = -6
 RT2_FLAG_MOMENTS = 1
 RT2_FLAG_FAST_MATH = 2
 RT2_FLAG_NO_BINNING = 4
+RT2_FLAG_GPU_LBVH = 8
 
 RT2_PRIM_SPHERE, RT2_PRIM_QUAD, RT2_PRIM_INSTANCE, RT2_PRIM_MEDIUM = 0, 1, 2, 3
 RT2_PRIM_NONE = 0xFFFFFFFF
@@ -102,7 +103,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("frames", C.c_uint64), ("launches", C.c_uint64),
                 ("gpu_ms_total", C.c_double), ("gpu_ms_extend", C.c_double), ("gpu_ms_shade", C.c_double),
-                ("gpu_ms_other", C.c_double), ("gpu_ms_finish", C.c_double), ("box_pair_tests", C.c_uint64),
+                ("gpu_ms_other", C.c_double), ("gpu_ms_finish", C.c_double), ("gpu_ms_bvh_build", C.c_double), ("box_pair_tests", C.c_uint64),
                 ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64)]
 
 
@@ -116,7 +117,7 @@ _P = C.c_void_p
 PROTOTYPES = {
     "rt2_scene_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(_P)]),
     "rt2_scene_load_string": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(_P)]),
-    "rt2_scene_synthetic_spheres": (C.c_int, [C.c_uint32, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "rt2_scene_synthetic_spheres": (C.c_int, [C.c_uint32, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "rt2_scene_destroy": (None, [_P]),
     "rt2_scene_get_desc": (C.c_int, [_P, C.POINTER(SceneDesc)]),
     "rt2_scene_set_dims": (C.c_int, [_P, C.c_int32, C.c_int32]),
@@ -138,6 +139,7 @@ PROTOTYPES = {
     "rt2_accum_device_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "rt2_set_frame_idx": (C.c_int, [_P, C.c_uint64]),
     "rt2_intersect": (C.c_int, [_P, _P, C.c_size_t, C.c_float, C.c_float, C.c_int, _P]),
+    "rt2_read_bvh": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rt2_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "rt2_set_profiling": (C.c_int, [_P, C.c_int]),
     "rt2_stream": (C.c_int, [_P, C.POINTER(_P)]),

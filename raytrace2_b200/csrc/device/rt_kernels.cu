@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 
+#include "rt_lbvh.hpp"
 #include "rt_render.hpp"
 #include "rt_shade.cuh"
 
@@ -368,6 +369,9 @@ struct Renderer::Impl {
   bool bin_present[kNumBins]{};
   std::vector<cudaEvent_t> prof_events;
   std::vector<int> prof_kind;
+  LbvhScratch lbvh_scratch;
+  void* d_build_prims{nullptr};
+  size_t cap_build_prims{0};
 };
 
 Renderer::Renderer() : impl_(new Impl) {}
@@ -381,6 +385,8 @@ Renderer::~Renderer() {
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.totals) cudaFree(m.totals);
+  if (m.d_build_prims) cudaFree(m.d_build_prims);
+  FreeLbvhScratch(&m.lbvh_scratch);
   if (m.ev_start) cudaEventDestroy(m.ev_start);
   if (m.ev_stop) cudaEventDestroy(m.ev_stop);
   for (cudaEvent_t e : m.prof_events) cudaEventDestroy(e);
@@ -473,16 +479,29 @@ int Renderer::UploadScene(const HostScene& scene) {
 #define UP(field, vec, cap)                                                   \
   rc = UploadBuf(&m.field, &m.cap, scene.vec, m.stream, &err_);               \
   if (rc != RT2_OK) return rc;
+  const bool gpu_bvh = (cfg_.flags & RT2_FLAG_GPU_LBVH) != 0;
+  if (!gpu_bvh && !scene.has_host_bvh) {
+    err_ = "this scene was created without a host BVH: create the renderer with RT2_FLAG_GPU_LBVH";
+    return RT2_ERR_STATE;
+  }
   UP(d_spheres, spheres, cap_spheres)
   UP(d_quads, quads, cap_quads)
   UP(d_xforms, xforms, cap_xforms)
-  UP(d_instances, instances, cap_instances)
-  UP(d_media, media, cap_media)
   UP(d_materials, materials, cap_materials)
   UP(d_textures, textures, cap_textures)
   UP(d_perlin, perlin, cap_perlin)
-  UP(d_prim_refs, prim_refs, cap_prim_refs)
-  UP(d_nodes, nodes, cap_nodes)
+  if (!gpu_bvh) {
+    UP(d_instances, instances, cap_instances)
+    UP(d_media, media, cap_media)
+    UP(d_prim_refs, prim_refs, cap_prim_refs)
+    UP(d_nodes, nodes, cap_nodes)
+    n_node_pairs_ = static_cast<uint32_t>(scene.nodes.size() / 2);
+    n_prim_refs_ = static_cast<uint32_t>(scene.prim_refs.size());
+    bvh_build_ms_ = 0;
+  } else {
+    rc = BuildTreesOnDevice(scene);
+    if (rc != RT2_OK) return rc;
+  }
 #undef UP
   scene_bytes_ = scene.spheres.size() * sizeof(rt2_sphere) + scene.quads.size() * sizeof(rt2_quad) +
                  scene.xforms.size() * sizeof(rt2_xform) + scene.instances.size() * sizeof(rt2_instance) +
@@ -500,7 +519,7 @@ int Renderer::UploadScene(const HostScene& scene) {
   d.perlin = static_cast<const rt2_perlin*>(m.d_perlin);
   d.prim_refs = static_cast<const uint32_t*>(m.d_prim_refs);
   d.nodes = static_cast<const float4*>(m.d_nodes);
-  d.tlas_root = scene.tlas_root;
+  d.tlas_root = gpu_bvh ? 0u : scene.tlas_root;  // device build: tree 0 (the TLAS) starts at pair 0
   d.n_media = static_cast<uint32_t>(scene.media.size());
   d.n_instances = static_cast<uint32_t>(scene.instances.size());
   d.min_inv_scale = scene.min_inv_scale;
@@ -519,6 +538,108 @@ int Renderer::UploadScene(const HostScene& scene) {
     }
   }
   cam_params_ = scene.cam;
+  return RT2_OK;
+}
+
+// RT2_FLAG_GPU_LBVH: every tree (world TLAS + one BLAS per instance) is built on the device from its leaf records.
+// Pair / reference index spaces are laid out here: media boundary references first, then the trees in order.
+int Renderer::BuildTreesOnDevice(const HostScene& scene) {
+  Impl& m = *impl_;
+  if (scene.tree_prims.size() != scene.instances.size() + 1) {
+    err_ = "scene carries no BVH build input";
+    return RT2_ERR_STATE;
+  }
+  // media boundary primitive lists keep their own slice of prim_refs
+  std::vector<uint32_t> prefix;
+  std::vector<rt2_medium> media = scene.media;
+  for (rt2_medium& md : media) {
+    const uint32_t first = static_cast<uint32_t>(prefix.size());
+    for (uint32_t i = 0; i < md.boundary_count; i++) prefix.push_back(scene.prim_refs[md.boundary_first + i]);
+    md.boundary_first = first;
+  }
+  std::vector<rt2_instance> instances = scene.instances;
+  const size_t n_trees = scene.tree_prims.size();
+  std::vector<uint32_t> pair_base(n_trees), ref_base(n_trees);
+  uint64_t pairs = 0, refs = prefix.size();
+  size_t max_n = 0;
+  for (size_t k = 0; k < n_trees; k++) {
+    const size_t n = scene.tree_prims[k].size();
+    pair_base[k] = static_cast<uint32_t>(pairs);
+    ref_base[k] = static_cast<uint32_t>(refs);
+    pairs += n > 1 ? n - 1 : 1;
+    refs += n;
+    max_n = n > max_n ? n : max_n;
+    if (k > 0) instances[k - 1].blas_root = pair_base[k];
+  }
+  if (pairs >= 0x7FFFFFF0ull || refs >= 0x07FFFFFFull) {
+    err_ = "scene too large for the 27-bit primitive / 31-bit node index fields";
+    return RT2_ERR_UNSUPPORTED;
+  }
+  int rc;
+  rc = UploadBuf(&m.d_instances, &m.cap_instances, instances, m.stream, &err_);
+  if (rc != RT2_OK) return rc;
+  rc = UploadBuf(&m.d_media, &m.cap_media, media, m.stream, &err_);
+  if (rc != RT2_OK) return rc;
+  auto ensure = [&](void** ptr, size_t* cap, size_t bytes) -> int {
+    if (bytes > *cap || *ptr == nullptr) {
+      if (*ptr) cudaFree(*ptr);
+      *ptr = nullptr;
+      *cap = 0;
+      RT2_CUDA(cudaMalloc(ptr, bytes > 0 ? bytes : 16));
+      *cap = bytes > 0 ? bytes : 16;
+    }
+    return RT2_OK;
+  };
+  rc = ensure(&m.d_nodes, &m.cap_nodes, pairs * 64);
+  if (rc != RT2_OK) return rc;
+  rc = ensure(&m.d_prim_refs, &m.cap_prim_refs, refs * 4);
+  if (rc != RT2_OK) return rc;
+  rc = ensure(&m.d_build_prims, &m.cap_build_prims, max_n * sizeof(BuildPrim));
+  if (rc != RT2_OK) return rc;
+  if (!prefix.empty()) RT2_CUDA(cudaMemcpyAsync(m.d_prim_refs, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, m.stream));
+  RT2_CUDA(cudaEventRecord(m.ev_start, m.stream));
+  for (size_t k = 0; k < n_trees; k++) {
+    const std::vector<BuildPrim>& tp = scene.tree_prims[k];
+    if (!tp.empty()) {
+      RT2_CUDA(cudaMemcpyAsync(m.d_build_prims, tp.data(), tp.size() * sizeof(BuildPrim), cudaMemcpyHostToDevice, m.stream));
+    }
+    rc = BuildLbvhOnDevice(static_cast<const BuildPrim*>(m.d_build_prims), static_cast<uint32_t>(tp.size()), pair_base[k], ref_base[k], m.d_nodes,
+                           static_cast<uint32_t*>(m.d_prim_refs), &m.lbvh_scratch, m.stream, &launches_, &err_);
+    if (rc != RT2_OK) return rc;
+    if (k + 1 < n_trees) RT2_CUDA(cudaStreamSynchronize(m.stream));  // d_build_prims is reused by the next tree
+  }
+  RT2_CUDA(cudaEventRecord(m.ev_stop, m.stream));
+  RT2_CUDA(cudaStreamSynchronize(m.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, m.ev_start, m.ev_stop);
+  bvh_build_ms_ = ms;
+  n_node_pairs_ = static_cast<uint32_t>(pairs);
+  n_prim_refs_ = static_cast<uint32_t>(refs);
+  return RT2_OK;
+}
+
+int Renderer::ReadBvh(rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs, size_t max_refs, uint32_t* n_pairs, uint32_t* n_refs,
+                      uint32_t* tlas_root) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  *n_pairs = n_node_pairs_;
+  *n_refs = n_prim_refs_;
+  *tlas_root = m.ds.tlas_root;
+  RT2_CUDA(cudaStreamSynchronize(m.stream));
+  if (nodes) {
+    if (max_nodes < 2ull * n_node_pairs_) {
+      err_ = "node buffer too small";
+      return RT2_ERR_INVALID_ARG;
+    }
+    RT2_CUDA(cudaMemcpy(nodes, m.d_nodes, 2ull * n_node_pairs_ * sizeof(rt2_bvh_node), cudaMemcpyDeviceToHost));
+  }
+  if (prim_refs) {
+    if (max_refs < n_prim_refs_) {
+      err_ = "prim_refs buffer too small";
+      return RT2_ERR_INVALID_ARG;
+    }
+    if (n_prim_refs_) RT2_CUDA(cudaMemcpy(prim_refs, m.d_prim_refs, static_cast<size_t>(n_prim_refs_) * 4, cudaMemcpyDeviceToHost));
+  }
   return RT2_OK;
 }
 
@@ -865,6 +986,7 @@ int Renderer::GetStats(rt2_stats* out) {
   out->gpu_ms_extend = prof_ms_[1];
   out->gpu_ms_shade = prof_ms_[2];
   out->gpu_ms_finish = prof_ms_[3];
+  out->gpu_ms_bvh_build = bvh_build_ms_;
   out->box_pair_tests = t[2];
   out->sphere_tests = t[3];
   out->quad_tests = t[4];

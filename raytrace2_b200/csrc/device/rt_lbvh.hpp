@@ -1,0 +1,22 @@
+// GPU LBVH builder interface (implementation: rt_lbvh.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "../host/scene_host.hpp"
+
+namespace rt2 {
+
+struct LbvhScratch {
+  void* ptr{nullptr};
+  size_t bytes{0};
+};
+
+// Builds one tree over the n device-resident (box, ref) records `d_prims` into node pairs [pair_base, pair_base + max(1, n-1))
+// of `d_nodes` and primitive references [ref_base, ref_base + n) of `d_prim_refs`.  Asynchronous on `stream`.
+int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, uint32_t ref_base, void* d_nodes, uint32_t* d_prim_refs,
+                      LbvhScratch* scratch, void* stream, uint64_t* launches, std::string* err);
+void FreeLbvhScratch(LbvhScratch* s);
+
+}  // namespace rt2

@@ -29,6 +29,8 @@ class Renderer {
   int AccumDevicePtr(void** ptr, size_t* n_floats);
   int Intersect(const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out);
   int GetStats(rt2_stats* out);
+  int ReadBvh(rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs, size_t max_refs, uint32_t* n_pairs, uint32_t* n_refs,
+              uint32_t* tlas_root);
   void* Stream();
   void SetProfiling(bool on) { profiling_ = on; }
   void SetFrameIdx(uint64_t f) { frame_idx_ = f; }
@@ -40,6 +42,7 @@ class Renderer {
 
  private:
   int RenderBatch(uint32_t n_frames);
+  int BuildTreesOnDevice(const HostScene& scene);
   void FreeState();
   Impl* impl_{nullptr};
   rt2_config cfg_{};
@@ -56,6 +59,9 @@ class Renderer {
   bool timing_pending_{false};
   size_t prof_used_{0};
   size_t scene_bytes_{0};
+  uint32_t n_node_pairs_{0};
+  uint32_t n_prim_refs_{0};
+  double bvh_build_ms_{0};
   std::string err_;
 };
 

@@ -6,6 +6,7 @@
 // the tree shape (result = arg-min over leaves of the raw reported t), so only culling quality changes.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "scene_host.hpp"
@@ -14,7 +15,23 @@ namespace rt2 {
 namespace {
 
 constexpr int kBins = 16;
-constexpr uint32_t kMaxLeaf = 4;
+// Leaf policy: a range of <= MaxLeaf() primitives becomes a leaf when the SAH says splitting does not pay, with one
+// node-pair visit costed as TravCost() primitive tests.  Overridable for tuning runs (RT2_BVH_MAX_LEAF, RT2_BVH_TRAV_COST).
+uint32_t MaxLeaf() {
+  static const uint32_t v = [] {
+    const char* e = std::getenv("RT2_BVH_MAX_LEAF");
+    int x = e ? std::atoi(e) : 4;
+    return static_cast<uint32_t>(x < 1 ? 1 : (x > 16 ? 16 : x));
+  }();
+  return v;
+}
+float TravCost() {
+  static const float v = [] {
+    const char* e = std::getenv("RT2_BVH_TRAV_COST");
+    return e ? static_cast<float>(std::atof(e)) : 2.5f;
+  }();
+  return v;
+}
 constexpr int kMaxDepth = 40;  // beyond this: median splits (<= 24 more levels for 16M prims; the device stack holds 64)
 
 struct Bounds {
@@ -132,7 +149,7 @@ size_t Split(BuildCtx& ctx, size_t begin, size_t end, const Bounds& bounds, bool
   if (best_axis >= 0) {
     float leaf_cost = bounds.HalfArea() * static_cast<float>(n);
     // traversal cost 1 box-pair test ~ 1.2 primitive tests
-    if (!has_instance && n <= kMaxLeaf && leaf_cost <= best_cost + 1.2f * bounds.HalfArea()) {
+    if (!has_instance && n <= MaxLeaf() && leaf_cost <= best_cost + TravCost() * bounds.HalfArea()) {
       *make_leaf = true;
       return begin;
     }
@@ -148,7 +165,7 @@ size_t Split(BuildCtx& ctx, size_t begin, size_t end, const Bounds& bounds, bool
     if (mid > begin && mid < end) return mid;
   }
   // all centroids coincide (or the binned split degenerated)
-  if (!has_instance && n <= kMaxLeaf) {
+  if (!has_instance && n <= MaxLeaf()) {
     *make_leaf = true;
     return begin;
   }

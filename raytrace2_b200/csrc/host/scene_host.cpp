@@ -450,6 +450,8 @@ struct Flattener {
     inst.top_level_node = top_idx;
     inst.blas_root = BuildBVH(own, sc);
     sc->instances.push_back(inst);
+    sc->tree_prims.resize(sc->instances.size() + 1);
+    sc->tree_prims[sc->instances.size()] = own;
     double sigma = 1.0;
     for (size_t i = sigma_first; i < level_sigma_.size(); i++) sigma *= level_sigma_[i];
     sc->min_inv_scale = std::fmin(sc->min_inv_scale, static_cast<float>(sigma * 0.9999));
@@ -487,6 +489,8 @@ int Compile(Builder& b, std::string* err) {
   sc->min_inv_scale = 1.0f;
   for (size_t i = 0; i < b.top.size(); i++) fl.FlattenNode(b.top[i], {}, &fl.tlas, static_cast<uint32_t>(i));
   sc->tlas_root = BuildBVH(fl.tlas, sc);
+  sc->tree_prims.resize(sc->instances.size() + 1);
+  sc->tree_prims[0] = fl.tlas;
   sc->UpdateCamera();
   (void)err;
   return RT2_OK;
@@ -928,7 +932,7 @@ int LoadAppSettings(const std::string& path, AppSettings* out, std::string* err)
 // radii ~U(0.2,1.0)*(1e6/n)^(1/3), ground sphere r=1e5, materials 80 % lambertian (albedo = xi*xi) / 15 % metal
 // (albedo U(0.5,1), fuzz U(0,0.5)) / 5 % dielectric 1.5, background (0.7,0.8,1.0), camera (0,600,-2200) -> origin,
 // fov 40, no defocus.  Every sphere is a top-level object (no transforms, no media).
-int MakeSyntheticSpheres(uint32_t n, uint64_t seed, int width, int height, HostScene* sc, std::string* err) {
+int MakeSyntheticSpheres(uint32_t n, uint64_t seed, int width, int height, bool build_host_bvh, HostScene* sc, std::string* err) {
   if (n == 0 || n > 0x0FFFFFF0u) {
     *err = "sphere count out of range";
     return RT2_ERR_INVALID_ARG;
@@ -984,7 +988,14 @@ int MakeSyntheticSpheres(uint32_t n, uint64_t seed, int width, int height, HostS
   }
   sc->n_top_level = n + 1;
   sc->span1_flags.assign(sc->n_top_level, 0);  // no media: Q2 is irrelevant
-  sc->tlas_root = BuildBVH(tlas, sc);
+  sc->has_host_bvh = build_host_bvh;
+  if (build_host_bvh) {
+    sc->tlas_root = BuildBVH(tlas, sc);
+  } else {
+    sc->tlas_root = 0;  // the tree is built on the device (RT2_FLAG_GPU_LBVH)
+  }
+  sc->tree_prims.resize(1);
+  sc->tree_prims[0] = std::move(tlas);
   sc->UpdateCamera();
   return RT2_OK;
 }

@@ -21,6 +21,13 @@ struct CameraParams {
   float focus_dist{10};
 };
 
+// BVH build input: one (box, primitive reference) record per leaf primitive of a tree.
+struct BuildPrim {
+  float bmin[3];
+  float bmax[3];
+  uint32_t ref;
+};
+
 struct HostScene {
   std::vector<rt2_sphere> spheres;
   std::vector<rt2_quad> quads;
@@ -35,6 +42,10 @@ struct HostScene {
   uint32_t tlas_root{0};
   uint32_t n_top_level{0};
   std::vector<uint8_t> span1_flags;  // per top-level node (Q2)
+  // Leaf records of every tree, kept for the device-side LBVH build (RT2_FLAG_GPU_LBVH): [0] = world TLAS,
+  // [1 + i] = BLAS of instance i.  has_host_bvh is false when the host SAH build was skipped (huge synthetic scenes).
+  std::vector<std::vector<BuildPrim>> tree_prims;
+  bool has_host_bvh{true};
   float background[3]{1, 1, 1};
   float min_inv_scale{1.f};
   int width{1600}, height{900};
@@ -51,7 +62,7 @@ int LoadSceneFile(const std::string& path, const std::string& data_dir, uint64_t
                   std::string* err);
 int LoadSceneString(const std::string& text, const std::string& data_dir, uint64_t perlin_seed, HostScene* out,
                     std::string* err);
-int MakeSyntheticSpheres(uint32_t n, uint64_t seed, int width, int height, HostScene* out, std::string* err);
+int MakeSyntheticSpheres(uint32_t n, uint64_t seed, int width, int height, bool build_host_bvh, HostScene* out, std::string* err);
 
 // AppSettings (src/Settings.hpp:5-11, Serialize.cpp:56-65)
 struct AppSettings {
@@ -65,11 +76,6 @@ int LoadAppSettings(const std::string& path, AppSettings* out, std::string* err)
 
 // BVH builder over (box, ref) leaves; appends node pairs to scene.nodes and refs to scene.prim_refs; returns the
 // root pair index.
-struct BuildPrim {
-  float bmin[3];
-  float bmax[3];
-  uint32_t ref;
-};
 uint32_t BuildBVH(std::vector<BuildPrim>& prims, HostScene* scene);
 
 }  // namespace rt2

@@ -73,13 +73,14 @@ int rt2_scene_load_string(const char* json_text, const char* data_dir, uint64_t 
   }
 }
 
-int rt2_scene_synthetic_spheres(uint32_t n_spheres, uint64_t seed, int32_t width, int32_t height, rt2_scene** out) {
+int rt2_scene_synthetic_spheres(uint32_t n_spheres, uint64_t seed, int32_t width, int32_t height, int32_t build_host_bvh,
+                                rt2_scene** out) {
   if (!out) return Fail(RT2_ERR_INVALID_ARG, "null argument");
   *out = nullptr;
   try {
     auto* s = new rt2_scene;
     std::string err;
-    int rc = rt2::MakeSyntheticSpheres(n_spheres, seed, width, height, &s->host, &err);
+    int rc = rt2::MakeSyntheticSpheres(n_spheres, seed, width, height, build_host_bvh != 0, &s->host, &err);
     if (rc != RT2_OK) {
       delete s;
       return Fail(rc, err);
@@ -208,6 +209,11 @@ int rt2_set_frame_idx(rt2_renderer* r, uint64_t frames) {
 int rt2_intersect(rt2_renderer* r, const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out) {
   if (n > 0 && (!rays || !out)) return Fail(RT2_ERR_INVALID_ARG, "null argument");
   RT2_FORWARD(r->impl.Intersect(rays, n, tmin, tmax, skip_media, out))
+}
+int rt2_read_bvh(rt2_renderer* r, rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs, size_t max_refs, uint32_t* n_pairs,
+                 uint32_t* n_refs, uint32_t* tlas_root) {
+  if (!n_pairs || !n_refs || !tlas_root) return Fail(RT2_ERR_INVALID_ARG, "null argument");
+  RT2_FORWARD(r->impl.ReadBvh(nodes, max_nodes, prim_refs, max_refs, n_pairs, n_refs, tlas_root))
 }
 int rt2_get_stats(rt2_renderer* r, rt2_stats* out) {
   if (!out) return Fail(RT2_ERR_INVALID_ARG, "null argument");

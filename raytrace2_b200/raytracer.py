@@ -54,10 +54,11 @@ class Scene:
         return cls(h.value)
 
     @classmethod
-    def synthetic_spheres(cls, n: int, seed: int = 20261018, width: int = 3840, height: int = 2160) -> "Scene":
+    def synthetic_spheres(cls, n: int, seed: int = 20261018, width: int = 3840, height: int = 2160, host_bvh: bool = True) -> "Scene":
+        """BASELINE config 5.  host_bvh=False skips the host SAH build; render such a scene with RT2_FLAG_GPU_LBVH."""
         lib = load_library()
         h = C.c_void_p()
-        check(lib.rt2_scene_synthetic_spheres(n, seed, width, height, C.byref(h)))
+        check(lib.rt2_scene_synthetic_spheres(n, seed, width, height, int(host_bvh), C.byref(h)))
         return cls(h.value)
 
     def __del__(self):
@@ -259,6 +260,16 @@ class RayTracer:
         st = _capi.Stats()
         check(self._lib.rt2_get_stats(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in _capi.Stats._fields_}
+
+    def read_bvh(self):
+        """(nodes, prim_refs, tlas_root) of the BVH the device traverses (host SAH upload or device LBVH build)."""
+        np_, nr, root = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(self._lib.rt2_read_bvh(self._h, None, 0, None, 0, C.byref(np_), C.byref(nr), C.byref(root)))
+        nodes = np.zeros(2 * np_.value, np.dtype(_capi.BvhNode))
+        refs = np.zeros(max(nr.value, 1), np.uint32)
+        check(self._lib.rt2_read_bvh(self._h, nodes.ctypes.data_as(C.c_void_p), nodes.size, refs.ctypes.data_as(C.c_void_p), refs.size,
+                                     C.byref(np_), C.byref(nr), C.byref(root)))
+        return nodes, refs[:nr.value], root.value
 
     def intersect(self, origins, directions, times=None, tmin: float = 0.001, tmax: float = 3.402823466e+38,
                   skip_media: bool = False) -> np.ndarray:

@@ -161,3 +161,61 @@ def test_media_sampling_statistics(native_lib, port_oracle):
     se = np.sqrt(g["t"][g_med].var() / g_med.sum() + r["t"][r_med].var() / r_med.sum())
     assert abs(mg - mr) < 4 * se, (mg, mr, se)
     assert (g["prim"][g_med] >> 28 == 3).all() and (g["normal"][g_med] == np.array([1, 0, 0], np.float32)).all()
+
+
+def _synthetic_to_json(scene, path):
+    """Dump a synthetic sphere scene (rt2_scene_synthetic_spheres) in the reference's current JSON format so the oracle can
+    load exactly the same spheres / materials."""
+    import json
+    d = scene.desc
+    mats = []
+    for m in scene.materials():
+        ty = int(m["type"])
+        if ty == 0:
+            mats.append({"type": "lambertian", "albedo": [float(x) for x in m["albedo"]]})
+        elif ty == 1:
+            mats.append({"type": "metal", "albedo": [float(x) for x in m["albedo"]], "fuzz": float(m["fuzz"])})
+        else:
+            mats.append({"type": "dielectric", "refraction_index": float(m["refraction_index"])})
+    prims = [{"type": "sphere", "center": [float(x) for x in s["center0"]], "radius": float(s["radius"]), "material": int(s["material"])}
+             for s in scene.spheres()]
+    cam = d.camera
+    doc = {"camera": {"fov": int(cam.vfov), "center": list(cam.center), "look_at": list(cam.look_at), "focus_distance": float(cam.focus_dist),
+                      "defocus_angle": float(cam.defocus_angle), "width": d.width, "aspect_ratio": d.width / d.height},
+           "background_color": list(d.background), "materials": mats, "primitives": prims,
+           "scene": [{"primitive": i} for i in range(len(prims))]}
+    with open(path, "w") as f:
+        json.dump(doc, f)
+
+
+def test_synthetic_sphere_scene_matches_oracle(native_lib, port_oracle, tmp_path):
+    """BASELINE config 5 (synthetic sphere BVH stress scene), scaled to 20 k spheres so the CPU oracle finishes in seconds."""
+    scene = rt.Scene.synthetic_spheres(20000, seed=11, width=320, height=180)
+    path = str(tmp_path / "synthetic.json")
+    _synthetic_to_json(scene, path)
+    port = port_oracle.PortScene(path, 16)
+    tracer = rt.RayTracer(scene)
+    o, d, tm = fixed_rays(scene, 100000, seed=3)
+    got = tracer.intersect(o, d, tm)
+    ref = port.intersect(o, d, tm)
+    # No instances here, so quirk Q1 cannot make another primitive win.  What remains is a float artefact of the reference:
+    # for a small sphere far from the ray origin (r < 1 at distance D ~ 3000) the discriminant h*h - a*c carries an
+    # absolute error ~ 2*eps*D^2 ~ 1, so Sphere::Hit (Sphere.cpp:8-15) reports "hits" up to ~1.5 units OUTSIDE the sphere.
+    # The reference accepts such a false positive whenever the ray crosses the box of the sphere's PARENT BVH node (its leaves
+    # are the spheres themselves, no per-sphere box test, BVH.cpp:50-55); our tighter per-leaf boxes cull it.  Bar: <= 3e-4
+    # of hits, and every disagreement must be such a geometric false positive of the reference.
+    leaf_map = leaf_to_prim_ref(path)
+    st = _compare(got, ref, np.ones(len(o), bool), "synthetic20k", 3e-4, leaf_map=leaf_map)
+    assert st["hits"] > 20000 and st["ties"] == 0
+    h = (got["material"] >= 0) & (ref["hit"] == 1)
+    diff = np.nonzero(h & (got["t"] != ref["t"]))[0]
+    sph = scene.spheres()
+
+    def off_sphere(point, prim_ref):
+        s = sph[int(prim_ref) & 0x0FFFFFFF]
+        dist = np.linalg.norm(point.astype(np.float64) - np.array(s["center0"], np.float64))
+        return dist > float(s["radius"]) * 1.002  # a true hit point lies ON its sphere (|p - c| = r up to ~3e-4 relative)
+    for i in diff:
+        # whichever side "won" with the smaller t did so with a point that is not on its sphere
+        assert off_sphere(ref["point"][i], leaf_map[ref["leaf"][i]]) or off_sphere(got["point"][i], got["prim"][i]), \
+            f"ray {i}: GPU and reference disagree on a genuine hit"
