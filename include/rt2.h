@@ -202,9 +202,12 @@ typedef struct rt2_renderer rt2_renderer;
 
 #define RT2_FLAG_MOMENTS 1u     /* also accumulate per-pixel sum of squares (z-score parity test) */
 #define RT2_FLAG_FAST_MATH 2u   /* FMA-contracted intersection arithmetic (default: bit-exact with the reference) */
-#define RT2_FLAG_NO_BINNING 4u  /* reserved */
+#define RT2_FLAG_NO_FUSED_SHADE 4u /* run k_finish_hit + one shade kernel per material bin instead of the fused
+                                     k_finish_shade (A/B and debugging; results are identical) */
 #define RT2_FLAG_GPU_LBVH 8u    /* build every BVH on the device (Morton codes + radix sort + Karras hierarchy) instead of
                                    uploading the host SAH trees */
+#define RT2_FLAG_SORT_RAYS 16u  /* reorder every bounce's ray queue by (direction octant, origin cell) before the traversal
+                                   (device radix sort); changes the traversal ORDER only, never a result */
 
 typedef struct rt2_config {
   int32_t device;            /* CUDA device ordinal */
@@ -234,6 +237,7 @@ typedef struct rt2_stats {
   uint64_t sphere_tests;
   uint64_t quad_tests;
   uint64_t instance_visits;
+  double gpu_ms_sort; /* ... of the ray-sort kernels (RT2_FLAG_SORT_RAYS) */
 } rt2_stats;
 
 typedef struct rt2_hit {

@@ -21,8 +21,9 @@ RT2_ERR_STATE = -6
 
 RT2_FLAG_MOMENTS = 1
 RT2_FLAG_FAST_MATH = 2
-RT2_FLAG_NO_BINNING = 4
+RT2_FLAG_NO_FUSED_SHADE = 4
 RT2_FLAG_GPU_LBVH = 8
+RT2_FLAG_SORT_RAYS = 16
 
 RT2_PRIM_SPHERE, RT2_PRIM_QUAD, RT2_PRIM_INSTANCE, RT2_PRIM_MEDIUM = 0, 1, 2, 3
 RT2_PRIM_NONE = 0xFFFFFFFF
@@ -104,7 +105,7 @@ class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("frames", C.c_uint64), ("launches", C.c_uint64),
                 ("gpu_ms_total", C.c_double), ("gpu_ms_extend", C.c_double), ("gpu_ms_shade", C.c_double),
                 ("gpu_ms_other", C.c_double), ("gpu_ms_finish", C.c_double), ("gpu_ms_bvh_build", C.c_double), ("box_pair_tests", C.c_uint64),
-                ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64)]
+                ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64), ("gpu_ms_sort", C.c_double)]
 
 
 class Hit(C.Structure):

@@ -15,7 +15,9 @@
 // grid-stride over the count they read there, so no host synchronisation happens inside a batch.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,6 +25,7 @@
 #include "rt_lbvh.hpp"
 #include "rt_render.hpp"
 #include "rt_shade.cuh"
+#include "rt_sort.cuh"
 
 namespace rt2dev {
 
@@ -39,12 +42,14 @@ struct FrameParams {
   uint32_t frame_base;    // global index of the batch's first frame
   uint32_t frame_stride;  // global frame of local frame lf = frame_base + lf * frame_stride
   uint32_t seed_lo, seed_hi;
+  unsigned long long pixels_magic;  // ceil(2^64 / pixels): slot / pixels == umul64hi(slot, magic) for slot < 2^32, pixels >= 2
 };
 
 __device__ __forceinline__ RngKey key_of_slot(const FrameParams& fp, uint32_t slot) {
   RngKey k;
-  k.pixel = slot % fp.pixels;
-  k.frame = fp.frame_base + (slot / fp.pixels) * fp.frame_stride;
+  const uint32_t lf = fp.pixels > 1u ? static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(slot), fp.pixels_magic)) : slot;
+  k.pixel = slot - lf * fp.pixels;
+  k.frame = fp.frame_base + lf * fp.frame_stride;
   k.seed_lo = fp.seed_lo;
   k.seed_hi = fp.seed_hi;
   return k;
@@ -121,14 +126,18 @@ struct BinQueues {
 
 // Extend, part 1: closest SURFACE for every queued ray of this bounce (persistent warps, dynamic ray fetch).
 // counters[7] of the bounce is the queue's fetch cursor (zeroed with the other counters at batch start).
-template <class M, bool kCount>
-__global__ void __launch_bounds__(kBlock) k_traverse(const DeviceScene S, uint32_t* __restrict__ counters,
+template <class M, bool kCount, int kVar = 0, int kMinBlocks = 1>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) k_traverse(const DeviceScene S, uint32_t* __restrict__ counters,
                                                      const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
-                                                     uint4* __restrict__ trav, unsigned long long* __restrict__ work_counters) {
+                                                     const uint32_t* __restrict__ order, uint32_t sort_min_rays,
+                                                     uint4* __restrict__ trav, unsigned long long* __restrict__ work_counters,
+                                                     int max_steps, int fetch_threshold) {
   const uint32_t n = counters[0];
   TravCounters cnt;
+  // queues below the threshold were not sorted (rt_sort.cuh): consume them in queue order
+  const uint32_t* ord = (order != nullptr && n >= sort_min_rays) ? order : nullptr;
   // scene.hittable_list.Hit(scene, r, Interval{0.001, kInfinity}, rec)  (RayTracer.cpp:25)
-  traverse_queue<M, kCount, kFetchThreshold>(S, n, ray_o, ray_d, 0.001f, kFltMax, counters + 7, trav, cnt);
+  traverse_queue<M, kCount, kFetchThreshold, kVar>(S, n, ray_o, ray_d, 0.001f, kFltMax, counters + 7, ord, trav, cnt, max_steps, fetch_threshold);
   if (kCount) {
     // warp-reduce, one atomic per warp and counter
     uint32_t v[4] = {cnt.box_pairs, cnt.spheres, cnt.quads, cnt.instances};
@@ -138,6 +147,20 @@ __global__ void __launch_bounds__(kBlock) k_traverse(const DeviceScene S, uint32
       for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
       if ((threadIdx.x & 31u) == 0u && x) atomicAdd(&work_counters[k], static_cast<unsigned long long>(x));
     }
+  }
+}
+
+// Extend, part 1 for tiny scenes (DeviceScene::flat_*): one thread per ray, uniform loops, no tree (traverse_flat).
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_traverse_flat(const DeviceScene S, const uint32_t* __restrict__ counters, uint32_t n_fixed,
+                                                          const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float tmin,
+                                                          float tmax, uint4* __restrict__ trav) {
+  const uint32_t n = counters ? counters[0] : n_fixed;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float4 o = ray_o[i], d = ray_d[i];
+    const Closest best = traverse_flat<M>(S, make_f3(o), make_f3(d), o.w, tmin, tmax);
+    trav[i] = make_uint4(__float_as_uint(best.t), best.prim, static_cast<uint32_t>(best.instance), 0u);
   }
 }
 
@@ -165,15 +188,131 @@ __global__ void __launch_bounds__(kBlock) k_finish_hit(const DeviceScene S, cons
   }
 }
 
+// Fused extend part 2 + shade: constant media against the closest surface, the winner's hit record, and — for every
+// material whose shading is cheap (everything except noise-textured ones) — Material::Scatter / Emit right here
+// (RayTracer.cpp:25-44), with the scattered ray appended to the next bounce's queue by one warp-aggregated atomic.
+// The hit record never goes to memory for these rays.  Materials flagged as deferred (rt2_material.pad != 0 on the
+// device: their texture chain reaches a Perlin / marble texture, ~1 kflop per evaluation) get their record written to
+// hit0 / hit1 and their index pushed into the material bin; k_shade_scatter / k_shade_terminal then run on those bins
+// only, so one marble ray does not stall its 31 warp-mates.
+//   counters[0] = queue size; counters[1..6] = deferred bins; next_counters[0] = rays emitted inline so far.
+template <class M, int kMinBlocks = 3>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const DeviceScene S, const FrameParams fp, uint32_t bounce, int emit_next,
+                                                         uint32_t* __restrict__ counters, uint32_t* __restrict__ next_counters,
+                                                         const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                         const float4* __restrict__ state, const uint4* __restrict__ trav,
+                                                         float4* __restrict__ hit0, float4* __restrict__ hit1, BinQueues bins,
+                                                         float4* __restrict__ out_o, float4* __restrict__ out_d,
+                                                         float4* __restrict__ out_state, uint32_t* __restrict__ sort_keys,
+                                                         float4* __restrict__ radiance) {
+  const uint32_t n = counters[0];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kBlock / 32;
+  constexpr int kClasses = 5;  // lambertian, textured lambertian, metal, dielectric, isotropic
+  __shared__ uint32_t s_off[kClasses][kWarps];
+  __shared__ uint32_t s_base;
+  const uint32_t n_tiles = (n + kBlock - 1) / kBlock;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {  // block-uniform trip count
+    const uint32_t i = tile * kBlock + threadIdx.x;
+    bool emit = false;
+    int cls = 0;
+    float4 no = make_float4(0, 0, 0, 0), nd = make_float4(0, 0, 0, 0), ns = make_float4(0, 0, 0, 0);
+    if (i < n) {
+      const float4 o = ray_o[i], d = ray_d[i];
+      const uint4 tr = trav[i];
+      const float4 st = state[i];
+      const uint32_t slot = __float_as_uint(st.w);
+      const RngKey key = key_of_slot(fp, slot);
+      HitOut h;
+      finish_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, bounce,
+                    false, h);
+      if (h.material < 0) {
+        // miss: T * background (RayTracer.cpp:25-27)
+        radiance[slot] = make_float4(st.x * S.background[0], st.y * S.background[1], st.z * S.background[2], 0.0f);
+      } else {
+        const float4 m0 = __ldg(S.materials + 2 * h.material), m1 = __ldg(S.materials + 2 * h.material + 1);
+        const uint32_t type = __float_as_uint(m0.x);
+        if (__float_as_uint(m1.w) != 0u) {
+          // deferred (noise-textured): record + bin, shaded by the per-bin kernels
+          hit0[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t);
+          hit1[i] = make_float4(h.n.x, h.n.y, h.n.z, __uint_as_float(static_cast<uint32_t>(h.material) | (h.front_face ? 0x80000000u : 0u)));
+          bin_push(counters, bins.base, bins.stride, bin_of_material(S, h.material), i);
+        } else if (type == RT2_MAT_DIFFUSE_LIGHT) {
+          const F3 c = texture_value_simple(S, __float_as_uint(m0.y), h.p);  // DiffuseLight::Emit (Material.cpp:71-74)
+          radiance[slot] = make_float4(st.x * c.x, st.y * c.y, st.z * c.z, 0.0f);
+        } else if (emit_next) {
+          const uint4 r = rng_draw(key, bounce, kStreamScatter);
+          F3 dir, att;
+          if (type == RT2_MAT_LAMBERTIAN || type == RT2_MAT_TEXTURE) {
+            // Material.cpp:47-69
+            const F3 u = unit_vector(u01(r.x), u01(r.y));
+            dir = {h.n.x + u.x, h.n.y + u.y, h.n.z + u.z};
+            if (near_zero(dir)) dir = h.n;
+            att = (type == RT2_MAT_LAMBERTIAN) ? F3{m1.x, m1.y, m1.z} : texture_value_simple(S, __float_as_uint(m0.y), h.p);
+            cls = (type == RT2_MAT_LAMBERTIAN) ? 0 : 1;
+          } else if (type == RT2_MAT_METAL) {
+            att = scatter<RT2_MAT_METAL>(S, m0, m1, make_f3(d), h.p, h.n, h.front_face, r, dir);
+            cls = 2;
+          } else if (type == RT2_MAT_DIELECTRIC) {
+            att = scatter<RT2_MAT_DIELECTRIC>(S, m0, m1, make_f3(d), h.p, h.n, h.front_face, r, dir);
+            cls = 3;
+          } else {  // RT2_MAT_ISOTROPIC, Material.cpp:76-83
+            cls = 4;
+            dir = unit_vector(u01(r.x), u01(r.y));
+            att = texture_value_simple(S, __float_as_uint(m0.y), h.p);
+          }
+          emit = true;
+          no = make_float4(h.p.x, h.p.y, h.p.z, o.w);
+          nd = make_float4(dir.x, dir.y, dir.z, 0.0f);
+          ns = make_float4(st.x * att.x, st.y * att.y, st.z * att.z, st.w);
+        }
+      }
+    }
+    // Append the tile's scattered rays to the next queue with ONE atomic per tile, grouped by material class inside the
+    // tile's slice: runs of the next queue come from neighbouring pixels / queue positions and share a material, so the
+    // warps of the next bounce start from similar places with similar direction distributions (a global stable
+    // compaction by chained scan and plain per-warp atomics were both measured slower, profiles/r01_notes.md).
+    unsigned my_mask = 0;
+#pragma unroll
+    for (int c = 0; c < kClasses; c++) {
+      const unsigned mc = __ballot_sync(0xFFFFFFFFu, emit && cls == c);
+      if (lane == 0) s_off[c][warp] = __popc(mc);
+      if (cls == c) my_mask = mc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      for (int c = 0; c < kClasses; c++)
+        for (int w = 0; w < kWarps; w++) {
+          const uint32_t v = s_off[c][w];
+          s_off[c][w] = acc;
+          acc += v;
+        }
+      s_base = acc ? atomicAdd(&next_counters[0], acc) : 0u;
+    }
+    __syncthreads();
+    if (emit) {
+      const uint32_t dst = s_base + s_off[cls][warp] + __popc(my_mask & ((1u << lane) - 1u));
+      out_o[dst] = no;
+      out_d[dst] = nd;
+      out_state[dst] = ns;
+      if (sort_keys) sort_keys[dst] = ray_sort_key(S, make_f3(no), make_f3(nd));
+    }
+    __syncthreads();  // s_off / s_base are rewritten by the next tile
+  }
+}
+
 // Paths that end here: miss -> background, emitter -> Emit (both faces).  radiance[slot] = throughput * colour.
 __global__ void __launch_bounds__(kBlock) k_shade_terminal(const DeviceScene S, uint32_t* __restrict__ counters,
                                                            uint32_t* __restrict__ next_counters, const uint32_t* __restrict__ queue,
                                                            const float4* __restrict__ state, const float4* __restrict__ hit0,
-                                                           const float4* __restrict__ hit1, float4* __restrict__ radiance) {
+                                                           const float4* __restrict__ hit1, float4* __restrict__ radiance, int fused) {
   const uint32_t n = counters[1];
   if (blockIdx.x == 0 && threadIdx.x == 0 && next_counters != nullptr) {
-    // every ray in a scattering bin produces exactly one ray for the next bounce
-    next_counters[0] = counters[2] + counters[3] + counters[4] + counters[5] + counters[6];
+    // every ray in a scattering bin produces exactly one ray for the next bounce; in fused mode (k_finish_shade) the
+    // bins hold the deferred rays only and next_counters[0] already counts the rays emitted inline
+    const uint32_t binned = counters[2] + counters[3] + counters[4] + counters[5] + counters[6];
+    next_counters[0] = fused ? next_counters[0] + binned : binned;
   }
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
@@ -199,9 +338,12 @@ __global__ void __launch_bounds__(kBlock) k_shade_scatter(const DeviceScene S, c
                                                           const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                           const float4* __restrict__ state, const float4* __restrict__ hit0,
                                                           const float4* __restrict__ hit1, float4* __restrict__ out_o,
-                                                          float4* __restrict__ out_d, float4* __restrict__ out_state) {
+                                                          float4* __restrict__ out_d, float4* __restrict__ out_state,
+                                                          uint32_t* __restrict__ sort_keys, const uint32_t* __restrict__ inline_count) {
   const uint32_t n = counters[1 + kBin];
-  uint32_t base = 0;
+  // fused mode: the deferred rays go behind the rays k_finish_shade emitted inline (k_shade_terminal, launched after
+  // the scatter kernels, folds the bin sizes into next_counters[0])
+  uint32_t base = inline_count ? inline_count[0] : 0u;
 #pragma unroll
   for (int b = 1; b < kBin; b++) base += counters[1 + b];
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -222,6 +364,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_scatter(const DeviceScene S, c
     out_o[dst] = make_float4(h0.x, h0.y, h0.z, time);
     out_d[dst] = make_float4(dir.x, dir.y, dir.z, 0.0f);
     out_state[dst] = make_float4(st.x * att.x, st.y * att.y, st.z * att.z, st.w);
+    if (sort_keys) sort_keys[dst] = ray_sort_key(S, make_f3(h0), dir);
   }
 }
 
@@ -310,7 +453,7 @@ __global__ void __launch_bounds__(kBlock) k_traverse_rays(const DeviceScene S, u
                                                           const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float tmin,
                                                           float tmax, uint4* __restrict__ trav) {
   TravCounters cnt;
-  traverse_queue<M, false, kFetchThreshold>(S, n, ray_o, ray_d, tmin, tmax, cursor, trav, cnt);
+  traverse_queue<M, false, kFetchThreshold>(S, n, ray_o, ray_d, tmin, tmax, cursor, nullptr, trav, cnt);
 }
 
 }  // namespace rt2dev
@@ -339,6 +482,13 @@ struct Renderer::Impl {
   void* d_xforms{nullptr};
   void* d_instances{nullptr};
   void* d_media{nullptr};
+  void* d_media_bounds{nullptr};
+  size_t cap_media_bounds{0};
+  void* d_flat_refs{nullptr};
+  void* d_flat_offsets{nullptr};
+  void* d_flat_bounds{nullptr};
+  size_t cap_flat_refs{0}, cap_flat_offsets{0}, cap_flat_bounds{0};
+  bool flat_mode{false};  // tiny scene: k_traverse_flat instead of the BVH walk
   void* d_materials{nullptr};
   void* d_textures{nullptr};
   void* d_perlin{nullptr};
@@ -369,6 +519,21 @@ struct Renderer::Impl {
   bool bin_present[kNumBins]{};
   std::vector<cudaEvent_t> prof_events;
   std::vector<int> prof_kind;
+  // ray sort (rt_sort.cuh)
+  uint32_t* sort_keys[2]{nullptr, nullptr};
+  uint32_t* sort_vals[2]{nullptr, nullptr};
+  uint32_t* sort_hist{nullptr};
+  uint32_t* sort_bin_base{nullptr};
+  int grid_sort{0};
+  int trav_variant{0};
+  int fs_blocks{3};
+  int trav_max_steps{8};  // node steps per round of the while-while traversal (measured: +12 % on the 1M-sphere scene, +1 % on book 2)
+  int trav_fetch_threshold{kFetchThreshold};
+  bool fused{true};               // k_finish_shade instead of k_finish_hit + per-bin shade kernels
+  bool deferred_present[kNumBins]{};  // fused mode: bins that can receive noise-textured (deferred) materials
+  bool sort_enabled{false};
+  uint32_t sort_min_rays{1u << 17};
+  uint32_t sort_max_bounce{16};
   LbvhScratch lbvh_scratch;
   void* d_build_prims{nullptr};
   size_t cap_build_prims{0};
@@ -381,7 +546,7 @@ Renderer::~Renderer() {
   cudaSetDevice(cfg_.device);
   FreeState();
   Impl& m = *impl_;
-  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes};
+  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_flat_bounds};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.totals) cudaFree(m.totals);
@@ -398,7 +563,9 @@ Renderer::~Renderer() {
 void Renderer::FreeState() {
   Impl& m = *impl_;
   void* bufs[] = {m.ray_o[0], m.ray_o[1], m.ray_d[0], m.ray_d[1], m.state[0], m.state[1], m.hit0, m.hit1, m.trav, m.counters,
-                  m.radiance, m.accum, m.accum_sq, m.mean_rgb, m.rgba8};
+                  m.radiance, m.accum, m.accum_sq, m.mean_rgb, m.rgba8, m.sort_keys[0], m.sort_keys[1], m.sort_vals[0], m.sort_vals[1],
+                  m.sort_hist, m.sort_bin_base};
+  m.sort_keys[0] = m.sort_keys[1] = m.sort_vals[0] = m.sort_vals[1] = m.sort_hist = m.sort_bin_base = nullptr;
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.bins.base) cudaFree(m.bins.base);
@@ -434,14 +601,34 @@ int Renderer::Init(const HostScene& scene, const rt2_config& cfg) {
   if (cfg_.frame_stride < 1) cfg_.frame_stride = 1;
   // persistent grids: resident blocks per SM x SM count
   int occ = 0;
+  if (const char* e = getenv("RT2_TRAV_VAR")) m.trav_variant = atoi(e);
+  if (const char* e = getenv("RT2_FS_BLOCKS")) m.fs_blocks = atoi(e);
+  if (const char* e = getenv("RT2_TRAV_STEPS")) m.trav_max_steps = atoi(e);
+  if (const char* e = getenv("RT2_TRAV_FETCH")) m.trav_fetch_threshold = atoi(e);
+  if (const char* e = getenv("RT2_L1_CARVEOUT")) {
+    const int c = atoi(e);  // percent of the unified L1/shared array reserved for shared memory
+    cudaFuncSetAttribute(k_traverse<ExactMath, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+    cudaFuncSetAttribute(k_traverse<ExactMath, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+    cudaFuncSetAttribute(k_traverse<ExactMath, false, 0, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+    cudaFuncSetAttribute(k_traverse<ExactMath, false, 1, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  }
   if (cfg_.flags & RT2_FLAG_FAST_MATH) {
     RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<FastMath, false>, kBlock, 0));
+  } else if (m.trav_variant >= 2) {
+    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false, 0, 5>, kBlock, 0));
   } else {
     RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false>, kBlock, 0));
   }
   if (occ < 1) occ = 1;
   m.grid_extend = sm_count_ * occ;
   m.grid_stream = sm_count_ * 8;
+  m.grid_sort = sm_count_ * 4;
+  m.sort_enabled = (cfg_.flags & RT2_FLAG_SORT_RAYS) != 0;
+  if (const char* e = getenv("RT2_SORT")) m.sort_enabled = atoi(e) != 0;
+  if (const char* e = getenv("RT2_SORT_MIN")) m.sort_min_rays = static_cast<uint32_t>(atol(e));
+  if (const char* e = getenv("RT2_SORT_MAXB")) m.sort_max_bounce = static_cast<uint32_t>(atol(e));
+  m.fused = (cfg_.flags & RT2_FLAG_NO_FUSED_SHADE) == 0;
+  if (const char* e = getenv("RT2_FUSED")) m.fused = atoi(e) != 0;
   int rc = UploadScene(scene);
   if (rc != RT2_OK) return rc;
   int w = cfg.width > 0 ? cfg.width : scene.width;
@@ -487,14 +674,62 @@ int Renderer::UploadScene(const HostScene& scene) {
   UP(d_spheres, spheres, cap_spheres)
   UP(d_quads, quads, cap_quads)
   UP(d_xforms, xforms, cap_xforms)
-  UP(d_materials, materials, cap_materials)
+  {
+    // device copy of the materials: pad != 0 marks materials whose texture chain reaches a noise texture (deferred
+    // shading in k_finish_shade); the ABI struct the caller sees is unchanged
+    std::vector<rt2_material> dev_mats = scene.materials;
+    for (int b = 0; b < kNumBins; b++) m.deferred_present[b] = false;
+    auto reaches_noise = [&](uint32_t tex) {
+      std::vector<uint32_t> todo{tex};
+      for (int guard = 0; guard < 64 && !todo.empty(); guard++) {
+        const uint32_t t = todo.back();
+        todo.pop_back();
+        if (t >= scene.textures.size()) continue;
+        const rt2_texture& tx = scene.textures[t];
+        if (tx.type == RT2_TEX_NOISE) return true;
+        if (tx.type == RT2_TEX_CHECKER) {
+          todo.push_back(tx.even_tex_idx);
+          todo.push_back(tx.odd_tex_idx);
+        }
+      }
+      return false;
+    };
+    for (rt2_material& mat : dev_mats) {
+      uint32_t flag = 0;
+      const bool textured = mat.type == RT2_MAT_TEXTURE || mat.type == RT2_MAT_DIFFUSE_LIGHT || mat.type == RT2_MAT_ISOTROPIC;
+      if (textured && reaches_noise(mat.tex_idx)) {
+        flag = 1;
+        m.deferred_present[mat.type == RT2_MAT_TEXTURE ? 2 : (mat.type == RT2_MAT_ISOTROPIC ? 5 : 0)] = true;
+      }
+      std::memcpy(&mat.pad, &flag, sizeof(flag));
+    }
+    rc = UploadBuf(&m.d_materials, &m.cap_materials, dev_mats, m.stream, &err_);
+    if (rc != RT2_OK) return rc;
+  }
   UP(d_textures, textures, cap_textures)
   UP(d_perlin, perlin, cap_perlin)
+  UP(d_media_bounds, media_bounds, cap_media_bounds)
   if (!gpu_bvh) {
     UP(d_instances, instances, cap_instances)
     UP(d_media, media, cap_media)
     UP(d_prim_refs, prim_refs, cap_prim_refs)
-    UP(d_nodes, nodes, cap_nodes)
+    {
+      // device node format: left_first of a LEAF holds the traversal entry (flag | (count-1) << 27 | first), so the
+      // node step of k_traverse uses it without decoding
+      std::vector<rt2_bvh_node> dev_nodes = scene.nodes;
+      for (rt2_bvh_node& nd : dev_nodes) {
+        if (nd.count > 0) {
+          if (nd.count > 16 || nd.left_first >= (1u << 27)) {
+            err_ = "BVH leaf does not fit the 4-bit count / 27-bit index entry";
+            return RT2_ERR_UNSUPPORTED;
+          }
+          nd.left_first = kLeafFlag | ((nd.count - 1u) << 27) | nd.left_first;
+        }
+      }
+      rc = UploadBuf(&m.d_nodes, &m.cap_nodes, dev_nodes, m.stream, &err_);
+      if (rc != RT2_OK) return rc;
+      RT2_CUDA(cudaStreamSynchronize(m.stream));  // dev_nodes is a temporary
+    }
     n_node_pairs_ = static_cast<uint32_t>(scene.nodes.size() / 2);
     n_prim_refs_ = static_cast<uint32_t>(scene.prim_refs.size());
     bvh_build_ms_ = 0;
@@ -514,6 +749,7 @@ int Renderer::UploadScene(const HostScene& scene) {
   d.xforms = static_cast<const float4*>(m.d_xforms);
   d.instances = static_cast<const uint4*>(m.d_instances);
   d.media = static_cast<const uint4*>(m.d_media);
+  d.media_bounds = static_cast<const float4*>(m.d_media_bounds);
   d.materials = static_cast<const float4*>(m.d_materials);
   d.textures = static_cast<const float4*>(m.d_textures);
   d.perlin = static_cast<const rt2_perlin*>(m.d_perlin);
@@ -524,6 +760,25 @@ int Renderer::UploadScene(const HostScene& scene) {
   d.n_instances = static_cast<uint32_t>(scene.instances.size());
   d.min_inv_scale = scene.min_inv_scale;
   for (int k = 0; k < 3; k++) d.background[k] = scene.background[k];
+  // ray-sort grid: robust world bounds of the top-level leaves (a far-away giant such as a r = 1000 ground sphere must
+  // not squeeze everything else into one cell): 0.5 / 99.5 percentiles of the box corners, 32 cells per axis
+  for (int k = 0; k < 3; k++) {
+    d.sort_lo[k] = 0.0f;
+    d.sort_scale[k] = 0.0f;
+  }
+  if (!scene.tree_prims.empty() && !scene.tree_prims[0].empty()) {
+    const std::vector<BuildPrim>& tp = scene.tree_prims[0];
+    const size_t cut = tp.size() / 200;
+    std::vector<float> lo(tp.size()), hi(tp.size());
+    for (int k = 0; k < 3; k++) {
+      for (size_t i = 0; i < tp.size(); i++) lo[i] = tp[i].bmin[k], hi[i] = tp[i].bmax[k];
+      std::nth_element(lo.begin(), lo.begin() + cut, lo.end());
+      std::nth_element(hi.begin(), hi.end() - 1 - cut, hi.end());
+      const float a = lo[cut], b = hi[hi.size() - 1 - cut];
+      d.sort_lo[k] = a;
+      d.sort_scale[k] = b > a ? 32.0f / (b - a) : 0.0f;
+    }
+  }
   // which material bins can ever be non-empty
   for (int b = 0; b < kNumBins; b++) m.bin_present[b] = false;
   m.bin_present[0] = true;
@@ -535,6 +790,57 @@ int Renderer::UploadScene(const HostScene& scene) {
       case RT2_MAT_DIELECTRIC: m.bin_present[4] = true; break;
       case RT2_MAT_ISOTROPIC: m.bin_present[5] = true; break;
       default: break;
+    }
+  }
+  // flat mode: list every leaf primitive by space when the scene is tiny
+  m.flat_mode = false;
+  d.flat_refs = nullptr;
+  d.flat_offsets = nullptr;
+  d.flat_inst_bounds = nullptr;
+  uint32_t flat_max = kFlatMaxPrims;
+  if (const char* e = getenv("RT2_FLAT_MAX")) flat_max = static_cast<uint32_t>(atol(e));
+  if (const char* e = getenv("RT2_FLAT")) flat_max = atoi(e) ? flat_max : 0u;
+  // (an explicit RT2_FLAG_GPU_LBVH asks for the device-built trees: keep the BVH walk)
+  if (!gpu_bvh && flat_max > 0 && scene.tree_prims.size() == scene.instances.size() + 1) {
+    std::vector<uint32_t> refs, offsets;
+    std::vector<float> bounds(scene.instances.size() * 8, 0.0f);
+    bool ok = true;
+    offsets.push_back(0);
+    for (const BuildPrim& bp : scene.tree_prims[0]) {
+      if (RT2_PRIM_TYPE(bp.ref) == RT2_PRIM_INSTANCE) {
+        const uint32_t j = RT2_PRIM_INDEX(bp.ref);
+        if (j >= scene.instances.size()) {
+          ok = false;
+          break;
+        }
+        for (int k = 0; k < 3; k++) {
+          bounds[8 * j + k] = bp.bmin[k];
+          bounds[8 * j + 4 + k] = bp.bmax[k];
+        }
+      } else {
+        refs.push_back(bp.ref);
+      }
+    }
+    offsets.push_back(static_cast<uint32_t>(refs.size()));
+    for (size_t j = 0; ok && j < scene.instances.size(); j++) {
+      for (const BuildPrim& bp : scene.tree_prims[1 + j]) {
+        if (RT2_PRIM_TYPE(bp.ref) == RT2_PRIM_INSTANCE) ok = false;  // nested instance references are flattened by the host; never expected
+        refs.push_back(bp.ref);
+      }
+      offsets.push_back(static_cast<uint32_t>(refs.size()));
+    }
+    if (ok && !refs.empty() && refs.size() <= flat_max) {
+      rc = UploadBuf(&m.d_flat_refs, &m.cap_flat_refs, refs, m.stream, &err_);
+      if (rc != RT2_OK) return rc;
+      rc = UploadBuf(&m.d_flat_offsets, &m.cap_flat_offsets, offsets, m.stream, &err_);
+      if (rc != RT2_OK) return rc;
+      rc = UploadBuf(&m.d_flat_bounds, &m.cap_flat_bounds, bounds, m.stream, &err_);
+      if (rc != RT2_OK) return rc;
+      RT2_CUDA(cudaStreamSynchronize(m.stream));  // the host vectors are temporaries
+      d.flat_refs = static_cast<const uint32_t*>(m.d_flat_refs);
+      d.flat_offsets = static_cast<const uint32_t*>(m.d_flat_offsets);
+      d.flat_inst_bounds = static_cast<const float4*>(m.d_flat_bounds);
+      m.flat_mode = true;
     }
   }
   cam_params_ = scene.cam;
@@ -632,6 +938,8 @@ int Renderer::ReadBvh(rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs
       return RT2_ERR_INVALID_ARG;
     }
     RT2_CUDA(cudaMemcpy(nodes, m.d_nodes, 2ull * n_node_pairs_ * sizeof(rt2_bvh_node), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < 2ull * n_node_pairs_; i++)  // device format -> ABI format (see UploadScene)
+      if (nodes[i].count > 0) nodes[i].left_first &= 0x07FFFFFFu;
   }
   if (prim_refs) {
     if (max_refs < n_prim_refs_) {
@@ -691,6 +999,14 @@ int Renderer::Resize(int w, int h) {
   if (cfg_.flags & RT2_FLAG_MOMENTS) RT2_CUDA(cudaMalloc(&m.accum_sq, P * sizeof(float4)));
   RT2_CUDA(cudaMalloc(&m.mean_rgb, P * 3 * sizeof(float)));
   RT2_CUDA(cudaMalloc(&m.rgba8, P * sizeof(uchar4)));
+  if (m.sort_enabled) {
+    for (int i = 0; i < 2; i++) {
+      RT2_CUDA(cudaMalloc(&m.sort_keys[i], N * sizeof(uint32_t)));
+      RT2_CUDA(cudaMalloc(&m.sort_vals[i], N * sizeof(uint32_t)));
+    }
+    RT2_CUDA(cudaMalloc(&m.sort_hist, static_cast<size_t>(m.grid_sort) * kSortBins * sizeof(uint32_t)));
+    RT2_CUDA(cudaMalloc(&m.sort_bin_base, kSortBins * sizeof(uint32_t)));
+  }
   return Reset();
 }
 
@@ -708,10 +1024,11 @@ int Renderer::Reset() {
 }
 
 template <int kType, int kBin>
-static void LaunchScatter(const Renderer::Impl& m, const FrameParams& fp, uint32_t bounce, uint32_t* ctr, int in, int out) {
+static void LaunchScatter(const Renderer::Impl& m, const FrameParams& fp, uint32_t bounce, uint32_t* ctr, int in, int out,
+                          uint32_t* sort_keys, const uint32_t* inline_count) {
   k_shade_scatter<kType, kBin><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, bounce, ctr, m.bins.q(kBin), m.ray_o[in], m.ray_d[in],
                                                                        m.state[in], m.hit0, m.hit1, m.ray_o[out], m.ray_d[out],
-                                                                       m.state[out]);
+                                                                       m.state[out], sort_keys, inline_count);
 }
 
 int Renderer::RenderBatch(uint32_t n_frames) {
@@ -732,6 +1049,7 @@ int Renderer::RenderBatch(uint32_t n_frames) {
   fp.frame_base = static_cast<uint32_t>(cfg_.frame_offset + frame_idx_ * cfg_.frame_stride);
   fp.seed_lo = static_cast<uint32_t>(cfg_.seed);
   fp.seed_hi = static_cast<uint32_t>(cfg_.seed >> 32);
+  fp.pixels_magic = P > 1 ? (~0ull / P + 1ull) : 0ull;  // ceil(2^64 / P), also when P is a power of two
   const bool exact = !(cfg_.flags & RT2_FLAG_FAST_MATH);
   const uint32_t max_depth = static_cast<uint32_t>(cfg_.max_depth);
 
@@ -761,35 +1079,89 @@ int Renderer::RenderBatch(uint32_t n_frames) {
     uint32_t* ctr = m.counters + static_cast<size_t>(b) * kCounterStride;
     uint32_t* next = m.counters + static_cast<size_t>(b + 1) * kCounterStride;
     const int out = in ^ 1;
+    // coherence order of this bounce's queue (keys were written by the scatter kernels of the previous bounce)
+    const bool sorted = m.sort_enabled && b >= 1 && b <= m.sort_max_bounce;
+    const bool sort_next = m.sort_enabled && b + 1 <= m.sort_max_bounce;
+    const uint32_t* order = nullptr;
+    if (sorted) {
+      prof(5);
+      const uint32_t smin = m.sort_min_rays;
+      k_sort_hist<<<m.grid_sort, kSortBlock, 0, m.stream>>>(ctr, smin, m.sort_keys[0], 0, m.sort_hist);
+      k_sort_scan<<<1, kSortBins, 0, m.stream>>>(ctr, smin, m.grid_sort, m.sort_hist, m.sort_bin_base);
+      k_sort_scatter<<<m.grid_sort, kSortBlock, 0, m.stream>>>(ctr, smin, m.sort_keys[0], nullptr, 0, m.sort_hist, m.sort_bin_base,
+                                                               m.sort_keys[1], m.sort_vals[1]);
+      k_sort_hist<<<m.grid_sort, kSortBlock, 0, m.stream>>>(ctr, smin, m.sort_keys[1], kSortDigitBits, m.sort_hist);
+      k_sort_scan<<<1, kSortBins, 0, m.stream>>>(ctr, smin, m.grid_sort, m.sort_hist, m.sort_bin_base);
+      k_sort_scatter<<<m.grid_sort, kSortBlock, 0, m.stream>>>(ctr, smin, m.sort_keys[1], m.sort_vals[1], kSortDigitBits, m.sort_hist,
+                                                               m.sort_bin_base, nullptr, m.sort_vals[0]);
+      launches_ += 6;
+      order = m.sort_vals[0];
+    }
     prof(1);
     unsigned long long* work = m.totals + 2;
-    if (exact) {
-      if (profiling_) k_traverse<ExactMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], m.trav, work);
-      else k_traverse<ExactMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], m.trav, work);
+    const uint32_t smin = m.sort_min_rays;
+    if (m.flat_mode) {
+      if (exact) k_traverse_flat<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, 0u, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav);
+      else k_traverse_flat<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, 0u, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav);
+    } else if (exact) {
+      if (profiling_) k_traverse<ExactMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
+      else if (m.trav_variant == 1) k_traverse<ExactMath, false, 1><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
+      else if (m.trav_variant == 2) k_traverse<ExactMath, false, 0, 5><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
+      else if (m.trav_variant == 3) k_traverse<ExactMath, false, 1, 5><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
+      else k_traverse<ExactMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
     } else {
-      if (profiling_) k_traverse<FastMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], m.trav, work);
-      else k_traverse<FastMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], m.trav, work);
+      if (profiling_) k_traverse<FastMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
+      else k_traverse<FastMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
     }
     prof(3);
-    if (exact) {
-      k_finish_hit<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, m.hit0,
-                                                                      m.hit1, m.bins);
-    } else {
-      k_finish_hit<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, m.hit0,
-                                                                     m.hit1, m.bins);
-    }
-    launches_ += 2;
-    prof(2);
     const bool last = (b + 1 == max_depth);  // RayColor(depth <= 0) returns black: nothing to scatter into
-    k_shade_terminal<<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, last ? nullptr : next, m.bins.q(0), m.state[in], m.hit0, m.hit1,
-                                                             m.radiance);
-    launches_++;
-    if (!last) {
-      if (m.bin_present[1]) LaunchScatter<RT2_MAT_LAMBERTIAN, 1>(m, fp, b, ctr, in, out), launches_++;
-      if (m.bin_present[2]) LaunchScatter<RT2_MAT_TEXTURE, 2>(m, fp, b, ctr, in, out), launches_++;
-      if (m.bin_present[3]) LaunchScatter<RT2_MAT_METAL, 3>(m, fp, b, ctr, in, out), launches_++;
-      if (m.bin_present[4]) LaunchScatter<RT2_MAT_DIELECTRIC, 4>(m, fp, b, ctr, in, out), launches_++;
-      if (m.bin_present[5]) LaunchScatter<RT2_MAT_ISOTROPIC, 5>(m, fp, b, ctr, in, out), launches_++;
+    uint32_t* keys = (sort_next && !last) ? m.sort_keys[0] : nullptr;
+    if (m.fused) {
+      // finish + inline shade; only noise-textured materials go through the bins
+      if (exact && m.fs_blocks == 2) {
+        k_finish_shade<ExactMath, 2><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
+                                                                             m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
+                                                                             m.ray_d[out], m.state[out], keys, m.radiance);
+      } else if (exact) {
+        k_finish_shade<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
+                                                                          m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
+                                                                          m.ray_d[out], m.state[out], keys, m.radiance);
+      } else {
+        k_finish_shade<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
+                                                                         m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
+                                                                         m.ray_d[out], m.state[out], keys, m.radiance);
+      }
+      launches_++;
+      prof(2);
+      if (!last) {
+        if (m.deferred_present[2]) LaunchScatter<RT2_MAT_TEXTURE, 2>(m, fp, b, ctr, in, out, keys, next), launches_++;
+        if (m.deferred_present[5]) LaunchScatter<RT2_MAT_ISOTROPIC, 5>(m, fp, b, ctr, in, out, keys, next), launches_++;
+      }
+      if (m.deferred_present[0] || ((m.deferred_present[2] || m.deferred_present[5]) && !last)) {
+        k_shade_terminal<<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, last ? nullptr : next, m.bins.q(0), m.state[in], m.hit0, m.hit1,
+                                                                 m.radiance, 1);
+        launches_++;
+      }
+    } else {
+      if (exact) {
+        k_finish_hit<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, m.hit0,
+                                                                        m.hit1, m.bins);
+      } else {
+        k_finish_hit<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, m.hit0,
+                                                                       m.hit1, m.bins);
+      }
+      launches_++;
+      prof(2);
+      k_shade_terminal<<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, last ? nullptr : next, m.bins.q(0), m.state[in], m.hit0, m.hit1,
+                                                               m.radiance, 0);
+      launches_++;
+      if (!last) {
+        if (m.bin_present[1]) LaunchScatter<RT2_MAT_LAMBERTIAN, 1>(m, fp, b, ctr, in, out, keys, nullptr), launches_++;
+        if (m.bin_present[2]) LaunchScatter<RT2_MAT_TEXTURE, 2>(m, fp, b, ctr, in, out, keys, nullptr), launches_++;
+        if (m.bin_present[3]) LaunchScatter<RT2_MAT_METAL, 3>(m, fp, b, ctr, in, out, keys, nullptr), launches_++;
+        if (m.bin_present[4]) LaunchScatter<RT2_MAT_DIELECTRIC, 4>(m, fp, b, ctr, in, out, keys, nullptr), launches_++;
+        if (m.bin_present[5]) LaunchScatter<RT2_MAT_ISOTROPIC, 5>(m, fp, b, ctr, in, out, keys, nullptr), launches_++;
+      }
     }
     in = out;
   }
@@ -805,7 +1177,7 @@ int Renderer::RenderBatch(uint32_t n_frames) {
       float ms = 0;
       cudaEventElapsedTime(&ms, m.prof_events[i], m.prof_events[i + 1]);
       int kind = m.prof_kind[i];
-      if (kind >= 0 && kind < 4) prof_ms_[kind] += ms;
+      if (kind >= 0 && kind < 6 && kind != 4) prof_ms_[kind] += ms;
     }
   }
   return RT2_OK;
@@ -953,7 +1325,15 @@ int Renderer::Intersect(const float* rays, size_t n, float tmin, float tmax, int
   const uint32_t grid = (n32 + kBlock - 1) / kBlock;
   const uint32_t tgrid = grid < static_cast<uint32_t>(m.grid_extend) ? grid : static_cast<uint32_t>(m.grid_extend);
   const uint32_t seed_lo = static_cast<uint32_t>(cfg_.seed), seed_hi = static_cast<uint32_t>(cfg_.seed >> 32);
-  if (cfg_.flags & RT2_FLAG_FAST_MATH) {
+  if (m.flat_mode) {
+    if (cfg_.flags & RT2_FLAG_FAST_MATH) {
+      k_traverse_flat<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, nullptr, n32, d_o, d_d, tmin, tmax, d_trav);
+      k_finish_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
+    } else {
+      k_traverse_flat<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, nullptr, n32, d_o, d_d, tmin, tmax, d_trav);
+      k_finish_intersect<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
+    }
+  } else if (cfg_.flags & RT2_FLAG_FAST_MATH) {
     k_traverse_rays<FastMath><<<tgrid, kBlock, 0, m.stream>>>(m.ds, n32, d_cursor, d_o, d_d, tmin, tmax, d_trav);
     k_finish_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
   } else {
@@ -987,6 +1367,7 @@ int Renderer::GetStats(rt2_stats* out) {
   out->gpu_ms_shade = prof_ms_[2];
   out->gpu_ms_finish = prof_ms_[3];
   out->gpu_ms_bvh_build = bvh_build_ms_;
+  out->gpu_ms_sort = prof_ms_[5];
   out->box_pair_tests = t[2];
   out->sphere_tests = t[3];
   out->quad_tests = t[4];

@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_emit(int n, uint32_t pair_b
     if (link & kChildLeaf) {
       mn = leaf_min[idx];
       mx = leaf_max[idx];
-      left_first = ref_base + idx;
+      left_first = kChildLeaf | (ref_base + idx);  // device node format: the traversal entry (leaf flag | (count-1) << 27 | first)
       count = 1;
     } else {
       mn = node_min[idx];
@@ -342,7 +342,7 @@ __global__ void k_lbvh_tiny(int n, uint32_t pair_base, uint32_t ref_base, const 
   for (int k = 0; k < 4; k++) out[k] = make_float4(nanv, nanv, nanv, __uint_as_float(0u));
   if (n == 1) {
     const rt2::BuildPrim p = prims[0];
-    out[0] = make_float4(p.bmin[0], p.bmin[1], p.bmin[2], __uint_as_float(ref_base));
+    out[0] = make_float4(p.bmin[0], p.bmin[1], p.bmin[2], __uint_as_float(kChildLeaf | ref_base));
     out[1] = make_float4(p.bmax[0], p.bmax[1], p.bmax[2], __uint_as_float(1u));
     prim_refs_out[0] = p.ref;
   }

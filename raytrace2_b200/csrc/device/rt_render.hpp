@@ -54,7 +54,7 @@ class Renderer {
   uint64_t frame_idx_{0};
   uint64_t launches_{0};
   double gpu_ms_total_{0};
-  double prof_ms_[4]{0, 0, 0, 0};
+  double prof_ms_[6]{0, 0, 0, 0, 0, 0};
   bool profiling_{false};
   bool timing_pending_{false};
   size_t prof_used_{0};

@@ -73,6 +73,19 @@ __device__ __forceinline__ F3 texture_value(const DeviceScene& S, uint32_t tex_i
   return {0.0f, 0.0f, 0.0f};
 }
 
+// texture_value for textures whose chain holds no noise texture (solid colours, checkers of solid colours): the cheap
+// subset the fused finish+shade kernel evaluates inline.  The host marks every material that can reach a noise texture
+// as deferred (Renderer::UploadScene), so the noise branch is never needed here.
+__device__ __forceinline__ F3 texture_value_simple(const DeviceScene& S, uint32_t tex_idx, F3 p) {
+  for (int depth = 0; depth < 8; depth++) {
+    const float4 t0 = __ldg(S.textures + 3 * tex_idx), t1 = __ldg(S.textures + 3 * tex_idx + 1);
+    if (__float_as_uint(t0.x) != RT2_TEX_CHECKER) return {t1.x, t1.y, t1.z};
+    int ix = static_cast<int>(floorf(t1.w * p.x)), iy = static_cast<int>(floorf(t1.w * p.y)), iz = static_cast<int>(floorf(t1.w * p.z));
+    tex_idx = ((ix + iy + iz) % 2 == 0) ? __float_as_uint(t0.y) : __float_as_uint(t0.z);
+  }
+  return {0.0f, 0.0f, 0.0f};
+}
+
 // math::NearZero (Math.hpp:61-64): |v_i| < 1e-8 (double literal)  <=>  |v_i| <= float(1e-8)
 __device__ __forceinline__ bool near_zero(F3 v) {
   const float e = 9.99999993922529e-09f;

@@ -19,6 +19,7 @@ struct DeviceScene {
   const float4* __restrict__ xforms;     // 6 x float4 per level   inv rows 0..2, model rows 0..2
   const uint4* __restrict__ instances;   // {chain_first, chain_len, blas_root, top_level}
   const uint4* __restrict__ media;       // 2 x uint4 per medium
+  const float4* __restrict__ media_bounds;  // 2 x float4 per medium: padded box of the boundary in the medium's space
   const float4* __restrict__ materials;  // 2 x float4 per material
   const float4* __restrict__ textures;   // 3 x float4 per texture
   const rt2_perlin* __restrict__ perlin;
@@ -29,6 +30,12 @@ struct DeviceScene {
   uint32_t n_instances;
   float min_inv_scale;
   float background[3];
+  // flat mode (tiny scenes, traverse_flat): every leaf primitive listed by space
+  const uint32_t* __restrict__ flat_refs;     // world primitives, then the primitives of instance 0, 1, ...
+  const uint32_t* __restrict__ flat_offsets;  // n_instances + 2 offsets into flat_refs
+  const float4* __restrict__ flat_inst_bounds;  // 2 x float4 per instance: world-space box
+  float sort_lo[3];     // ray-sort grid (rt_sort.cuh): robust scene bounds, 32 cells per axis
+  float sort_scale[3];
 };
 
 constexpr float kFltMax = 3.402823466e+38f;  // kInfinity (Defs.hpp:17)
@@ -177,12 +184,14 @@ struct TravCounters {
 // reconverging with __syncwarp() between the phases, so the expensive exact-arithmetic primitive tests run with many
 // lanes instead of whichever lanes happen to reach a leaf in the same iteration.  Lanes whose ray is finished write
 // the result and idle; when fewer than kFetchThreshold lanes are busy the warp pulls new rays from the queue with one
-// atomic.  Results go to trav_out[ray] = {t bits, prim ref, instance, 0}.
-template <class M, bool kCount, int kFetchThreshold>
+// atomic.  `order` (optional) is the permutation in which the queue is consumed.  Results go to
+// trav_out[ray] = {t bits, prim ref, instance, 0}.
+template <class M, bool kCount, int kFetchThreshold, int kVar = 0>
 __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n, const float4* __restrict__ ray_o,
                                                const float4* __restrict__ ray_d, float tmin, float tmax,
-                                               uint32_t* __restrict__ next_ray, uint4* __restrict__ trav_out,
-                                               TravCounters& cnt) {
+                                               uint32_t* __restrict__ next_ray, const uint32_t* __restrict__ order,
+                                               uint4* __restrict__ trav_out, TravCounters& cnt, int max_steps = 1 << 30,
+                                               int fetch_threshold = kFetchThreshold) {
   const unsigned kFull = 0xFFFFFFFFu;
   const unsigned lane = threadIdx.x & 31u;
   uint32_t stack[kStackSize];
@@ -209,7 +218,9 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
   auto pop = [&]() {
     while (true) {
       if (sp == 0) {
-        trav_out[ray_idx] = make_uint4(__float_as_uint(best.t), best.prim, static_cast<uint32_t>(best.instance), 0u);
+        const uint4 res = make_uint4(__float_as_uint(best.t), best.prim, static_cast<uint32_t>(best.instance), 0u);
+        if (kVar & 1) __stcs(trav_out + ray_idx, res);  // streaming: the queues must not evict the scene from L1
+        else trav_out[ray_idx] = res;
         active = false;
         return;
       }
@@ -233,10 +244,12 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         if (static_cast<int>(lane) == leader) base = atomicAdd(next_ray, __popc(idle));
         base = __shfl_sync(kFull, base, leader);
         if (!active) {
-          const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
-          if (idx < n) {
+          const uint32_t pos = base + __popc(idle & ((1u << lane) - 1u));
+          if (pos < n) {
+            const uint32_t idx = order ? order[pos] : pos;  // rt_sort.cuh: coherence order of the queue
             ray_idx = idx;
-            const float4 wo = ray_o[idx], wd = ray_d[idx];
+            const float4 wo = (kVar & 1) ? __ldcs(ray_o + idx) : ray_o[idx];
+            const float4 wd = (kVar & 1) ? __ldcs(ray_d + idx) : ray_d[idx];
             time = wo.w;
             set_space(make_f3(wo), make_f3(wd));
             // An instanced leaf reports t in model units (= world t * |M^-1 d|): a world-space box at parameter t_w can
@@ -259,28 +272,31 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
 
     // ---- traverse until too few lanes are busy ----
     while (true) {
-      // phase 1: interior nodes
-      while (active && !(cur & kLeafFlag)) {
+      // phase 1: interior nodes (at most max_steps per round, so that lanes holding a leaf do not wait for a long descent)
+      for (int step = 0; step < max_steps && active && !(cur & kLeafFlag); step++) {
         const float4* np = S.nodes + static_cast<size_t>(cur) * 4;
         const float4 a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
         if (kCount) cnt.box_pairs++;
+        // conservative culling: near is shrunk by 1e-6 relative before it is compared with far and with the (scaled)
+        // closest hit so far; an empty slot has NaN bounds -> far is NaN -> never entered
         const float bound = best.t * cur_cull;
         float t0x = fmaf(a0.x, inv.x, oid.x), t1x = fmaf(a1.x, inv.x, oid.x);
         float t0y = fmaf(a0.y, inv.y, oid.y), t1y = fmaf(a1.y, inv.y, oid.y);
         float t0z = fmaf(a0.z, inv.z, oid.z), t1z = fmaf(a1.z, inv.z, oid.z);
         const float near0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
         const float far0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-        const bool h0 = (near0 * 0.9999995f <= far0 * 1.0000005f) && (near0 * 0.9999995f <= bound);
+        const float n0 = near0 * 0.999999f;
+        const bool h0 = (n0 <= far0) && (n0 <= bound);
         t0x = fmaf(b0.x, inv.x, oid.x), t1x = fmaf(b1.x, inv.x, oid.x);
         t0y = fmaf(b0.y, inv.y, oid.y), t1y = fmaf(b1.y, inv.y, oid.y);
         t0z = fmaf(b0.z, inv.z, oid.z), t1z = fmaf(b1.z, inv.z, oid.z);
         const float near1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
         const float far1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-        const bool h1 = (near1 * 0.9999995f <= far1 * 1.0000005f) && (near1 * 0.9999995f <= bound);
-        const uint32_t c0 = __float_as_uint(a1.w), c1 = __float_as_uint(b1.w);
-        // entry: interior -> child pair index; leaf -> flag | (count-1) << 27 | first
-        const uint32_t e0 = c0 ? (kLeafFlag | ((c0 - 1u) << 27) | __float_as_uint(a0.w)) : __float_as_uint(a0.w);
-        const uint32_t e1 = c1 ? (kLeafFlag | ((c1 - 1u) << 27) | __float_as_uint(b0.w)) : __float_as_uint(b0.w);
+        const float n1 = near1 * 0.999999f;
+        const bool h1 = (n1 <= far1) && (n1 <= bound);
+        // device node format (rt_kernels.cu UploadScene / rt_lbvh.cu): .w of the min corner is the traversal entry itself:
+        // interior -> child pair index; leaf -> flag | (count-1) << 27 | first
+        const uint32_t e0 = __float_as_uint(a0.w), e1 = __float_as_uint(b0.w);
         if (h0 && h1) {
           const bool swap = near1 < near0;
           cur = swap ? e1 : e0;
@@ -295,7 +311,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
       }
       __syncwarp();
       // phase 2: leaves
-      if (active) {
+      if (active && (cur & kLeafFlag)) {
         const uint32_t first = cur & 0x07FFFFFFu;
         const uint32_t count = ((cur >> 27) & 0xFu) + 1u;
         bool entered = false;
@@ -338,32 +354,170 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
       __syncwarp();
       const unsigned busy = __ballot_sync(kFull, active);
       if (busy == 0u) break;
-      if (!exhausted && __popc(busy) < kFetchThreshold) break;
+      if (!exhausted && __popc(busy) < fetch_threshold) break;
     }
   }
+}
+
+// Closest surface for TINY scenes (a Cornell box: 18 quads, 2 instances): no tree at all.  Every ray tests every world
+// primitive, then enters every instance whose world box it touches and tests all of that instance's primitives — the
+// same arg-min over leaves as traverse_queue, but with a loop whose trip counts and primitive types are
+// identical for all 32 lanes of a warp.  On SIMT hardware that beats a BVH walk whose lanes diverge at every step
+// (measured on B200: Cornell box 2.5x faster extend stage, profiles/r01_notes.md); the host picks this path when the
+// scene has at most kFlatMaxPrims leaf primitives in total.
+constexpr uint32_t kFlatMaxPrims = 40;
+
+template <class M>
+__device__ __forceinline__ void flat_test_range(const DeviceScene& S, uint32_t first, uint32_t last, F3 o, F3 d, float a, float time,
+                                                float tmin, int32_t inst, bool lane_on, Closest& best) {
+  for (uint32_t k = first; k < last; k++) {
+    const uint32_t ref = __ldg(S.flat_refs + k);  // warp-uniform
+    const uint32_t idx = RT2_PRIM_INDEX(ref);
+    float t;
+    bool h;
+    if (RT2_PRIM_TYPE(ref) == RT2_PRIM_SPHERE) {
+      h = sphere_hit<M>(__ldg(S.spheres + 2 * idx), __ldg(S.spheres + 2 * idx + 1), o, d, a, time, tmin, best.t, t);
+    } else {
+      h = quad_hit<M>(S.quads + 5 * idx, o, d, tmin, best.t, t);
+    }
+    if (h && lane_on) {
+      best.t = t;
+      best.prim = ref;
+      best.instance = inst;
+    }
+  }
+}
+
+template <class M>
+__device__ __forceinline__ Closest traverse_flat(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, float tmax) {
+  Closest best{tmax, RT2_PRIM_NONE, -1};
+  flat_test_range<M>(S, __ldg(S.flat_offsets + 0), __ldg(S.flat_offsets + 1), wo, wd, vdot<M>(wd, wd), time, tmin, -1, true, best);
+  const float ix = safe_rcp(wd.x), iy = safe_rcp(wd.y), iz = safe_rcp(wd.z);
+  for (uint32_t j = 0; j < S.n_instances; j++) {
+    // conservative world-box test of the whole ray (no bound by best.t: an instanced leaf reports t in model units)
+    const float4 bmn = __ldg(S.flat_inst_bounds + 2 * j), bmx = __ldg(S.flat_inst_bounds + 2 * j + 1);
+    const float ax = (bmn.x - wo.x) * ix, bx = (bmx.x - wo.x) * ix;
+    const float ay = (bmn.y - wo.y) * iy, by = (bmx.y - wo.y) * iy;
+    const float az = (bmn.z - wo.z) * iz, bz = (bmx.z - wo.z) * iz;
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    const bool touch = tn * 0.999999f <= tf;
+    if (!__any_sync(__activemask(), touch)) continue;
+    const uint4 in = __ldg(S.instances + j);
+    const RaySpace ms = to_chain_space<M>(S, in.x, in.y, RaySpace{wo, wd});
+    flat_test_range<M>(S, __ldg(S.flat_offsets + 1 + j), __ldg(S.flat_offsets + 2 + j), ms.o, ms.d, vdot<M>(ms.d, ms.d), time, tmin,
+                       static_cast<int32_t>(j), touch, best);
+  }
+  return best;
 }
 
 // ConstantMedium::Hit (ConstantMedium.cpp:14-58), split in two: the boundary queries (deterministic, independent of the
 // caller's interval) and the free-path draw against the current [tmin, tmax].  A medium in a span-1 leaf of the
 // reference BVH has Hit() called twice (quirk Q2): both calls see identical boundary records, so they are computed once.
+// Roots of one boundary primitive along the ray, independent of any interval: Sphere::Hit's two roots (Sphere.cpp:13-24)
+// or Quad::Hit's plane parameter when the point lies inside the quad (Quad.cpp:19-35); NaN = no root.
+template <class M>
+__device__ __forceinline__ void boundary_roots(const DeviceScene& S, uint32_t ref, F3 o, F3 d, float a, float time, float& r_lo,
+                                               float& r_hi, bool& is_sphere) {
+  const float nanv = __int_as_float(0x7FC00000);
+  const uint32_t idx = RT2_PRIM_INDEX(ref);
+  r_lo = nanv;
+  r_hi = nanv;
+  is_sphere = RT2_PRIM_TYPE(ref) == RT2_PRIM_SPHERE;
+  if (is_sphere) {
+    const float4 s0 = __ldg(S.spheres + 2 * idx), s1 = __ldg(S.spheres + 2 * idx + 1);
+    F3 center = ray_at<M>(make_f3(s0), make_f3(s1), time);
+    F3 oc = vsub<M>(center, o);
+    float h = vdot<M>(d, oc);
+    float c = M::sub(vdot<M>(oc, oc), M::mul(s0.w, s0.w));
+    float disc = M::sub(M::mul(h, h), M::mul(a, c));
+    if (disc < 0.0f) return;
+    float sqrtd = M::sqrt(disc);
+    r_lo = M::div(M::sub(h, sqrtd), a);
+    r_hi = M::div(M::add(h, sqrtd), a);
+  } else {
+    float t;
+    if (quad_hit<M>(S.quads + 5 * idx, o, d, -kFltMax, kFltMax, t)) r_lo = t;
+  }
+}
+// What <primitive>::Hit(r, Interval(lo, kInfinity)) reports for the roots above: spheres use the open interval and prefer
+// the near root (Sphere.cpp:19-24), quads the closed one (Quad.cpp:27).  NaN = miss.
+__device__ __forceinline__ float boundary_candidate(float r_lo, float r_hi, bool is_sphere, float lo) {
+  const float nanv = __int_as_float(0x7FC00000);
+  if (is_sphere) {
+    if (lo < r_lo && r_lo < kFltMax) return r_lo;
+    if (lo < r_hi && r_hi < kFltMax) return r_hi;
+    return nanv;
+  }
+  return (lo <= r_lo && r_lo <= kFltMax) ? r_lo : nanv;
+}
+
+// The two boundary queries of ConstantMedium::Hit (ConstantMedium.cpp:18-24):
+//   boundary_->Hit(r, Interval::kUniverse, rec1);  boundary_->Hit(r, Interval(rec1.t + 0.0001, kInfinity), rec2)
+// A closest-hit query over a list returns the minimum of the per-primitive candidates (HittableList.cpp:8-22: shrinking
+// tmax), and a primitive's roots do not depend on the interval, so for short boundaries (a sphere, a box of 6 quads) the
+// roots are computed ONCE and both queries are answered from them — same values bit for bit, half the arithmetic.
+constexpr uint32_t kBoundaryRootsMax = 6;
 template <class M>
 __device__ __forceinline__ bool medium_boundary(const DeviceScene& S, const uint4 m0, F3 o, F3 d, float a, float time, float& t1,
                                                 float& t2) {
-  // boundary_->Hit(r, Interval::kUniverse, rec1)
+  if (m0.w == 1u) {  // a single primitive (the usual sphere-bounded medium)
+    float lo, hi;
+    bool sph;
+    boundary_roots<M>(S, __ldg(S.prim_refs + m0.z), o, d, a, time, lo, hi, sph);
+    t1 = boundary_candidate(lo, hi, sph, -kFltMax);
+    if (!(t1 <= kFltMax)) return false;
+    const float t1_eps = static_cast<float>(static_cast<double>(t1) + 0.0001);
+    t2 = boundary_candidate(lo, hi, sph, t1_eps);
+    return t2 <= kFltMax;
+  }
+  if (m0.w <= kBoundaryRootsMax) {
+    float lo[kBoundaryRootsMax], hi[kBoundaryRootsMax];
+    bool sph[kBoundaryRootsMax];
+    float q1 = kFltMax;
+    bool any1 = false;
+#pragma unroll
+    for (uint32_t k = 0; k < kBoundaryRootsMax; k++) {
+      lo[k] = hi[k] = __int_as_float(0x7FC00000);
+      sph[k] = false;
+      if (k < m0.w) {
+        boundary_roots<M>(S, __ldg(S.prim_refs + m0.z + k), o, d, a, time, lo[k], hi[k], sph[k]);
+        const float c = boundary_candidate(lo[k], hi[k], sph[k], -kFltMax);
+        if (c <= q1) {  // NaN compares false
+          q1 = c;
+          any1 = true;
+        }
+      }
+    }
+    if (!any1) return false;
+    t1 = q1;
+    // the sum is formed in double, then stored as float
+    const float t1_eps = static_cast<float>(static_cast<double>(t1) + 0.0001);
+    float q2 = kFltMax;
+    bool any2 = false;
+#pragma unroll
+    for (uint32_t k = 0; k < kBoundaryRootsMax; k++) {
+      const float c = boundary_candidate(lo[k], hi[k], sph[k], t1_eps);
+      if (c <= q2) {
+        q2 = c;
+        any2 = true;
+      }
+    }
+    t2 = q2;
+    return any2;
+  }
+  // long boundary lists: two sequential queries
   if (!list_hit<M>(S, m0.z, m0.w, o, d, a, time, -kFltMax, kFltMax, t1)) return false;
-  // boundary_->Hit(r, Interval(rec1.t + 0.0001, kInfinity), rec2): the sum is formed in double, then stored as float
   const float t1_eps = static_cast<float>(static_cast<double>(t1) + 0.0001);
   return list_hit<M>(S, m0.z, m0.w, o, d, a, time, t1_eps, kFltMax, t2);
 }
 template <class M>
-__device__ __forceinline__ bool medium_draw(float neg_inv_density, float ray_len, float t1, float t2, float tmin, float tmax, float xi,
-                                            float& t_out) {
+__device__ __forceinline__ bool medium_draw(float hit_dist, float ray_len, float t1, float t2, float tmin, float tmax, float& t_out) {
   t1 = fmaxf(t1, tmin);
   t2 = fminf(t2, tmax);
   if (t1 >= t2) return false;
   t1 = fmaxf(t1, 0.0f);
   const float dist_inside = M::mul(M::sub(t2, t1), ray_len);
-  const float hit_dist = M::mul(neg_inv_density, logf(xi));
   if (hit_dist > dist_inside) return false;
   t_out = M::add(t1, M::div(hit_dist, ray_len));
   return true;
@@ -387,22 +541,37 @@ __device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, f
 
   // constant media (few per scene): each draws its free path against the current best raw t
   int32_t medium_hit = -1;
+  uint4 draw = make_uint4(0, 0, 0, 0);
+  bool have_draw = false;
   if (!skip_media) {
     for (uint32_t m = 0; m < S.n_media; m++) {
       const uint4 m0 = __ldg(S.media + 2 * m), m1 = __ldg(S.media + 2 * m + 1);
       RaySpace rs = to_chain_space<M>(S, m1.x, m1.y, RaySpace{wo, wd});
       const float a = vdot<M>(rs.d, rs.d);
+      const float ray_len = M::sqrt(a);  // glm::length(r.direction)
+      // one Philox call serves two media: .xy for even m, .zw for odd m
+      if ((m & 1u) == 0u || !have_draw) {
+        draw = rng_draw(key, bounce, kStreamMedium + (m >> 1));
+        have_draw = true;
+      }
+      const uint32_t xi1 = (m & 1u) ? draw.z : draw.x, xi2 = (m & 1u) ? draw.w : draw.y;
+      // hit_distance = neg_inv_density * std::log(RandReal()) (ConstantMedium.cpp:42), one draw per Hit() call
+      const float hd1 = M::mul(__uint_as_float(m0.x), logf(u01(xi1)));
+      const float hd2 = m1.z ? M::mul(__uint_as_float(m0.x), logf(u01(xi2))) : kFltMax;
+      // Early out (no boundary roots needed): the segment inside the medium is never longer than the caller's
+      // interval, so a free path beyond (tmax - max(tmin, 0)) * |d| (+ rounding slack) cannot scatter.  Thin fog that
+      // encloses the whole scene (book 2: r = 5000, density 1e-4) is rejected here for ~9 rays out of 10.
+      const float span = (best.t - fmaxf(tmin, 0.0f)) * ray_len * 1.00001f;
+      if (hd1 > span && hd2 > span) continue;
       float t1, t2;
       if (!medium_boundary<M>(S, m0, rs.o, rs.d, a, time, t1, t2)) continue;
-      const float ray_len = M::sqrt(a);  // glm::length(r.direction)
-      const uint4 r = rng_draw(key, bounce, kStreamMedium + m);
       float t;
-      if (medium_draw<M>(__uint_as_float(m0.x), ray_len, t1, t2, tmin, best.t, u01(r.x), t)) {
+      if (medium_draw<M>(hd1, ray_len, t1, t2, tmin, best.t, t)) {
         best.t = t;
         medium_hit = static_cast<int32_t>(m);
       }
       if (m1.z) {  // span-1 leaf of the reference BVH: Hit() runs twice, the second against the shrunken interval
-        if (medium_draw<M>(__uint_as_float(m0.x), ray_len, t1, t2, tmin, best.t, u01(r.y), t)) {
+        if (medium_draw<M>(hd2, ray_len, t1, t2, tmin, best.t, t)) {
           best.t = t;
           medium_hit = static_cast<int32_t>(m);
         }

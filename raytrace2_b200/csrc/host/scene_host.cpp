@@ -371,6 +371,19 @@ struct Flattener {
       m.sample_twice = sc->span1_flags[top_idx];
       m.top_level_node = top_idx;
       sc->media.push_back(m);
+      // conservative box of the boundary (device-side early out of ConstantMedium::Hit, rt_trace.cuh finish_hit)
+      Box3 mb = PrimBounds(*sc, def.refs[0]);
+      for (uint32_t r : def.refs) {
+        const Box3 pb = PrimBounds(*sc, r);
+        for (int k = 0; k < 3; k++) {
+          mb.mn[k] = std::min(mb.mn[k], pb.mn[k]);
+          mb.mx[k] = std::max(mb.mx[k], pb.mx[k]);
+        }
+      }
+      for (int k = 0; k < 3; k++) sc->media_bounds.push_back(mb.mn[k]);
+      sc->media_bounds.push_back(0.f);
+      for (int k = 0; k < 3; k++) sc->media_bounds.push_back(mb.mx[k]);
+      sc->media_bounds.push_back(0.f);
       return;
     }
     for (uint32_t r : def.refs) target->push_back(MakeBuildPrim(PrimBounds(*sc, r), r));

@@ -34,6 +34,7 @@ struct HostScene {
   std::vector<rt2_xform> xforms;
   std::vector<rt2_instance> instances;
   std::vector<rt2_medium> media;
+  std::vector<float> media_bounds;  // 8 floats per medium: padded AABB of its boundary in the medium's own space (min xyz 0, max xyz 0)
   std::vector<rt2_material> materials;
   std::vector<rt2_texture> textures;
   std::vector<rt2_perlin> perlin;
