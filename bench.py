@@ -17,6 +17,7 @@ against the measured HBM peak; `cpu_baseline` = the reference CPU renderer timed
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -33,6 +34,12 @@ DEFAULT_SCENE = "book2_final_scene_10000_samples"
 # algorithmic HBM bytes per ray of k_traverse: ray origin+time 16 + direction 16 read, closest-surface
 # record 16 written
 EXTEND_BYTES_PER_RAY = 16 + 16 + 16
+# DRAM bytes per ray of k_traverse from the committed `ncu --set full` capture (profiles/r01c_ncu_summary.txt): used for
+# roofline.traffic = per-ray traffic x rays per launch; None until a capture is recorded
+EXTEND_DRAM_BYTES_PER_RAY_NCU = 35.3
+# arithmetic credited per unit of algorithmic work: AABB slab test 30, sphere test 30 (to the
+# discriminant; a lower bound), quad test 57, instance visit 42
+FLOP_AABB, FLOP_SPHERE, FLOP_QUAD, FLOP_INSTANCE = 30, 30, 57, 42
 
 
 def parse_args():
@@ -274,7 +281,8 @@ def run_ours(args):
     scene_bytes = (d.n_spheres * 32 + d.n_quads * 80 + d.n_xforms * 96 + d.n_instances * 16 + d.n_media * 32 + d.n_materials * 32 +
                    d.n_textures * 48 + d.n_perlin * 7168 + d.n_prim_refs * 4 + d.n_node_pairs * 64)
     e2e = {"value": float(e2e_r.item()) / float(e2e_t.item()) * 1e-6, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene_bytes),
-           "d2h_bytes_per_step": int(W * H * 3 * 4), "host_memory": "pageable"}
+           "d2h_bytes_per_step": int(W * H * 3 * 4),
+           "host_memory": "pinned staging arena inside the library (cudaMallocHost), host buffers on both sides of the C ABI"}
     del e0
 
     # ---- roofline of the dominant kernel: per-kernel CUDA-event split over extra (untimed) profiled steps ----
@@ -288,11 +296,37 @@ def run_ours(args):
     ext_ms = ps["gpu_ms_extend"]
     prof_total = ps["gpu_ms_extend"] + ps["gpu_ms_shade"] + ps["gpu_ms_other"] + ps["gpu_ms_finish"]
     achieved = ps["rays"] * EXTEND_BYTES_PER_RAY / (ext_ms * 1e-3) * 1e-9 if ext_ms > 0 else 0.0
-    roofline = {"kernel": "k_traverse", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_ray": EXTEND_BYTES_PER_RAY,
+    prof_steps = min(args.steps, 4)
+    n_trav_launches = max(1, prof_steps * args.max_depth)  # one k_traverse launch per bounce and batch
+    rays_per_launch = ps["rays"] / n_trav_launches
+    kernel_name = "k_traverse_flat" if ps["box_pair_tests"] == 0 else "k_traverse"
+    roofline = {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"],
+                "traffic": (EXTEND_DRAM_BYTES_PER_RAY_NCU * rays_per_launch) if (EXTEND_DRAM_BYTES_PER_RAY_NCU and kernel_name == "k_traverse") else None,
+                "traffic_note": "ncu dram__bytes_read+write per ray (profiles/) x mean rays per launch; algorithmic = 48 B/ray x the same",
+                "peak_source": peak_src, "algorithmic_bytes_per_ray": EXTEND_BYTES_PER_RAY,
+                "algorithmic_bytes_per_launch": EXTEND_BYTES_PER_RAY * rays_per_launch,
+                "avg_launch_ms": ext_ms / n_trav_launches,
                 "share_of_step": ext_ms / prof_total if prof_total > 0 else None,
-                "note": "k_traverse is FP32-issue / latency bound (scene lives in L1/L2); see DESIGN.md and profiles/"}
+                "note": "the extend kernel is instruction-issue bound under divergence (scene lives in L1/L2), so its HBM fraction is small "
+                        "by construction; roofline_fp32 below is the roofline that binds it (DESIGN.md §4, profiles/)"}
+    # the roofline that actually binds the extend stage: credited arithmetic of the algorithmic work done by active lanes
+    # (device counters of the profiling build) against the FP32 FMA peak measured on this GPU by our micro-benchmark
+    fp32_peak = C.c_double(0.0)
+    rt.load_library().rt2_measure_fp32_peak(local_rank, C.byref(fp32_peak))
+    flops = (2 * ps["box_pair_tests"] * FLOP_AABB + ps["sphere_tests"] * FLOP_SPHERE + ps["quad_tests"] * FLOP_QUAD +
+             ps["instance_visits"] * FLOP_INSTANCE)
+    ach_tf = flops / (ext_ms * 1e-3) * 1e-12 if ext_ms > 0 else 0.0
+    roofline_fp32 = {"kernel": kernel_name, "bound": "fp32", "achieved": ach_tf, "peak": fp32_peak.value, "unit": "TFLOP/s",
+                     "frac": ach_tf / fp32_peak.value if fp32_peak.value > 0 else None,
+                     "peak_source": "measured here (rt2_measure_fp32_peak: FMA micro-benchmark, 2 flop per FMA)",
+                     "flop_per_ray": flops / max(ps["rays"], 1),
+                     "per_ray": {"aabb_tests": 2 * ps["box_pair_tests"] / max(ps["rays"], 1), "sphere_tests": ps["sphere_tests"] / max(ps["rays"], 1),
+                                 "quad_tests": ps["quad_tests"] / max(ps["rays"], 1), "instance_visits": ps["instance_visits"] / max(ps["rays"], 1)},
+                     "note": "credited flops per SURVEY Appendix C (30 / AABB test, 30 / sphere, 57 / quad, 42 / instance visit) of the work "
+                             "done by ACTIVE lanes; unavailable (0) for the flat extend kernel, which has no counters"}
+    kernel_split = {"extend_ms": ps["gpu_ms_extend"], "finish_shade_ms": ps["gpu_ms_finish"], "deferred_shade_ms": ps["gpu_ms_shade"],
+                    "sort_ms": ps["gpu_ms_sort"], "other_ms": ps["gpu_ms_other"], "steps": prof_steps}
 
     line = {
         "metric": "Mrays/s", "value": rays_all / (ms_all * 1e-3) * 1e-6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -303,7 +337,8 @@ def run_ours(args):
                    "intersection_math": "fast (FMA)" if args.fast_math else "exact (bit-identical with the reference)",
                    "l2": "wavefront state per step (%.0f MB) exceeds L2; no explicit flush" % (W * H * S * 184 / 1e6),
                    "parallelism": f"sample-partition x{world}" if world > 1 else "single GPU"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "roofline": roofline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "roofline": roofline, "roofline_fp32": roofline_fp32,
+        "kernel_split_profiled": kernel_split,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.scene.startswith("synthetic:"):

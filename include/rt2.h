@@ -301,6 +301,9 @@ int rt2_app_run(int argc, const char* const* argv, const char* settings_path, co
 const char* rt2_last_error(void);
 int rt2_abi_version(void);
 int rt2_device_count(void);
+/* Measured FP32 FMA peak of a device in TFLOP/s (micro-benchmark kernel; the roofline denominator of the instruction-bound
+ * kernels). */
+int rt2_measure_fp32_peak(int32_t device, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -150,6 +150,7 @@ PROTOTYPES = {
     "rt2_last_error": (C.c_char_p, []),
     "rt2_abi_version": (C.c_int, []),
     "rt2_device_count": (C.c_int, []),
+    "rt2_measure_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
 }
 
 _lib = None

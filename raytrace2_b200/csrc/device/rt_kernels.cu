@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kBlock) k_finish_hit(const DeviceScene S, cons
 // hit0 / hit1 and their index pushed into the material bin; k_shade_scatter / k_shade_terminal then run on those bins
 // only, so one marble ray does not stall its 31 warp-mates.
 //   counters[0] = queue size; counters[1..6] = deferred bins; next_counters[0] = rays emitted inline so far.
-template <class M, int kMinBlocks = 3>
+template <class M, int kMinBlocks = 4>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const DeviceScene S, const FrameParams fp, uint32_t bounce, int emit_next,
                                                          uint32_t* __restrict__ counters, uint32_t* __restrict__ next_counters,
                                                          const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   constexpr int kWarps = kBlock / 32;
   constexpr int kClasses = 5;  // lambertian, textured lambertian, metal, dielectric, isotropic
-  __shared__ uint32_t s_off[kClasses][kWarps];
-  __shared__ uint32_t s_base;
+  __shared__ uint32_t s_off[2][kClasses][kWarps];
+  __shared__ uint32_t s_base[2];
+  int parity = 0;
   const uint32_t n_tiles = (n + kBlock - 1) / kBlock;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {  // block-uniform trip count
     const uint32_t i = tile * kBlock + threadIdx.x;
@@ -272,33 +273,42 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
     // tile's slice: runs of the next queue come from neighbouring pixels / queue positions and share a material, so the
     // warps of the next bounce start from similar places with similar direction distributions (a global stable
     // compaction by chained scan and plain per-warp atomics were both measured slower, profiles/r01_notes.md).
+    uint32_t(*off)[kWarps] = s_off[parity];
     unsigned my_mask = 0;
 #pragma unroll
     for (int c = 0; c < kClasses; c++) {
       const unsigned mc = __ballot_sync(0xFFFFFFFFu, emit && cls == c);
-      if (lane == 0) s_off[c][warp] = __popc(mc);
+      if (lane == 0) off[c][warp] = __popc(mc);
       if (cls == c) my_mask = mc;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t acc = 0;
-      for (int c = 0; c < kClasses; c++)
-        for (int w = 0; w < kWarps; w++) {
-          const uint32_t v = s_off[c][w];
-          s_off[c][w] = acc;
-          acc += v;
-        }
-      s_base = acc ? atomicAdd(&next_counters[0], acc) : 0u;
+    if (warp == 0) {
+      // exclusive scan of the kClasses x kWarps counts (class-major) by one warp: two entries per lane
+      uint32_t* flat = &off[0][0];
+      const uint32_t v0 = 2 * lane < kClasses * kWarps ? flat[2 * lane] : 0u;
+      const uint32_t v1 = 2 * lane + 1 < kClasses * kWarps ? flat[2 * lane + 1] : 0u;
+      uint32_t incl = v0 + v1;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= static_cast<unsigned>(o)) incl += y;
+      }
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      uint32_t base = 0;
+      if (lane == 0 && total) base = atomicAdd(&next_counters[0], total);
+      const uint32_t excl = incl - (v0 + v1);
+      if (2 * lane < kClasses * kWarps) flat[2 * lane] = excl;
+      if (2 * lane + 1 < kClasses * kWarps) flat[2 * lane + 1] = excl + v0;
+      if (lane == 0) s_base[parity] = base;
     }
     __syncthreads();
     if (emit) {
-      const uint32_t dst = s_base + s_off[cls][warp] + __popc(my_mask & ((1u << lane) - 1u));
+      const uint32_t dst = s_base[parity] + off[cls][warp] + __popc(my_mask & ((1u << lane) - 1u));
       out_o[dst] = no;
       out_d[dst] = nd;
       out_state[dst] = ns;
       if (sort_keys) sort_keys[dst] = ray_sort_key(S, make_f3(no), make_f3(nd));
     }
-    __syncthreads();  // s_off / s_base are rewritten by the next tile
+    parity ^= 1;  // the next tile uses the other copy of s_off / s_base: no third barrier
   }
 }
 
@@ -489,6 +499,9 @@ struct Renderer::Impl {
   void* d_flat_bounds{nullptr};
   size_t cap_flat_refs{0}, cap_flat_offsets{0}, cap_flat_bounds{0};
   bool flat_mode{false};  // tiny scene: k_traverse_flat instead of the BVH walk
+  // pinned host staging: scene uploads are packed into it (true async H2D), read-backs land in it (true async D2H)
+  char* h_stage{nullptr};
+  size_t h_stage_cap{0}, h_stage_used{0};
   void* d_materials{nullptr};
   void* d_textures{nullptr};
   void* d_perlin{nullptr};
@@ -526,7 +539,7 @@ struct Renderer::Impl {
   uint32_t* sort_bin_base{nullptr};
   int grid_sort{0};
   int trav_variant{0};
-  int fs_blocks{3};
+  int fs_blocks{4};  // resident blocks per SM the fused kernel is compiled for (4: 64 registers, a few spills; measured +1-2 %)
   int trav_max_steps{8};  // node steps per round of the while-while traversal (measured: +12 % on the 1M-sphere scene, +1 % on book 2)
   int trav_fetch_threshold{kFetchThreshold};
   bool fused{true};               // k_finish_shade instead of k_finish_hit + per-bin shade kernels
@@ -550,6 +563,7 @@ Renderer::~Renderer() {
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.totals) cudaFree(m.totals);
+  if (m.h_stage) cudaFreeHost(m.h_stage);
   if (m.d_build_prims) cudaFree(m.d_build_prims);
   FreeLbvhScratch(&m.lbvh_scratch);
   if (m.ev_start) cudaEventDestroy(m.ev_start);
@@ -636,8 +650,15 @@ int Renderer::Init(const HostScene& scene, const rt2_config& cfg) {
   return Resize(w, h);
 }
 
+constexpr size_t kStageMax = 512ull << 20;  // scenes beyond this are copied straight from pageable memory
+
+static int EnsureStage(Renderer::Impl& m, size_t bytes, std::string* err);
+
+// Copies `v` to the device buffer *dptr (grown on demand).  Small scenes go through the pinned staging arena so that the
+// copy is a real asynchronous DMA from page-locked memory; the arena is recycled at the start of every UploadScene and
+// the stream is synchronised at its end.
 template <class T>
-static int UploadBuf(void** dptr, size_t* cap, const std::vector<T>& v, cudaStream_t stream, std::string* err) {
+static int UploadBuf(Renderer::Impl& m, void** dptr, size_t* cap, const std::vector<T>& v, std::string* err) {
   size_t bytes = v.size() * sizeof(T);
   if (bytes > *cap || *dptr == nullptr) {
     if (*dptr) cudaFree(*dptr);
@@ -650,11 +671,36 @@ static int UploadBuf(void** dptr, size_t* cap, const std::vector<T>& v, cudaStre
     *cap = alloc;
   }
   if (bytes) {
-    cudaError_t e = cudaMemcpyAsync(*dptr, v.data(), bytes, cudaMemcpyHostToDevice, stream);
+    const void* src = v.data();
+    const size_t off = (m.h_stage_used + 255) & ~static_cast<size_t>(255);
+    if (m.h_stage && off + bytes <= m.h_stage_cap) {
+      std::memcpy(m.h_stage + off, v.data(), bytes);
+      src = m.h_stage + off;
+      m.h_stage_used = off + bytes;
+    }
+    cudaError_t e = cudaMemcpyAsync(*dptr, src, bytes, cudaMemcpyHostToDevice, m.stream);
     if (e != cudaSuccess) {
       *err = std::string("cudaMemcpyAsync(scene buffer) failed: ") + cudaGetErrorString(e);
       return RT2_ERR_CUDA;
     }
+  }
+  return RT2_OK;
+}
+
+static int EnsureStage(Renderer::Impl& m, size_t bytes, std::string* err) {
+  if (bytes > kStageMax) return RT2_OK;  // too large to mirror in page-locked memory: UploadBuf falls back to pageable copies
+  if (bytes > m.h_stage_cap) {
+    if (m.h_stage) cudaFreeHost(m.h_stage);
+    m.h_stage = nullptr;
+    m.h_stage_cap = 0;
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) {
+      *err = std::string("cudaMallocHost(staging) failed: ") + cudaGetErrorString(e);
+      return RT2_ERR_CUDA;
+    }
+    m.h_stage = static_cast<char*>(p);
+    m.h_stage_cap = bytes;
   }
   return RT2_OK;
 }
@@ -664,8 +710,21 @@ int Renderer::UploadScene(const HostScene& scene) {
   RT2_CUDA(cudaSetDevice(cfg_.device));
   int rc;
 #define UP(field, vec, cap)                                                   \
-  rc = UploadBuf(&m.field, &m.cap, scene.vec, m.stream, &err_);               \
+  rc = UploadBuf(m, &m.field, &m.cap, scene.vec, &err_);                      \
   if (rc != RT2_OK) return rc;
+  {
+    // staging arena: every buffer uploaded below (+ 256-byte alignment slack per buffer)
+    size_t total = scene.spheres.size() * sizeof(rt2_sphere) + scene.quads.size() * sizeof(rt2_quad) + scene.xforms.size() * sizeof(rt2_xform) +
+                   scene.instances.size() * sizeof(rt2_instance) + scene.media.size() * sizeof(rt2_medium) +
+                   scene.materials.size() * sizeof(rt2_material) + scene.textures.size() * sizeof(rt2_texture) +
+                   scene.perlin.size() * sizeof(rt2_perlin) + scene.prim_refs.size() * sizeof(uint32_t) +
+                   scene.nodes.size() * sizeof(rt2_bvh_node) + scene.media_bounds.size() * sizeof(float) +
+                   (kFlatMaxPrims + scene.instances.size() * 9 + 8) * sizeof(uint32_t) + 32 * 256;
+    RT2_CUDA(cudaStreamSynchronize(m.stream));  // earlier copies out of the arena
+    rc = EnsureStage(m, total, &err_);
+    if (rc != RT2_OK) return rc;
+    m.h_stage_used = 0;
+  }
   const bool gpu_bvh = (cfg_.flags & RT2_FLAG_GPU_LBVH) != 0;
   if (!gpu_bvh && !scene.has_host_bvh) {
     err_ = "this scene was created without a host BVH: create the renderer with RT2_FLAG_GPU_LBVH";
@@ -703,7 +762,8 @@ int Renderer::UploadScene(const HostScene& scene) {
       }
       std::memcpy(&mat.pad, &flag, sizeof(flag));
     }
-    rc = UploadBuf(&m.d_materials, &m.cap_materials, dev_mats, m.stream, &err_);
+    rc = UploadBuf(m, &m.d_materials, &m.cap_materials, dev_mats, &err_);
+    RT2_CUDA(cudaStreamSynchronize(m.stream));  // dev_mats is a temporary (needed when the arena is bypassed)
     if (rc != RT2_OK) return rc;
   }
   UP(d_textures, textures, cap_textures)
@@ -726,7 +786,7 @@ int Renderer::UploadScene(const HostScene& scene) {
           nd.left_first = kLeafFlag | ((nd.count - 1u) << 27) | nd.left_first;
         }
       }
-      rc = UploadBuf(&m.d_nodes, &m.cap_nodes, dev_nodes, m.stream, &err_);
+      rc = UploadBuf(m, &m.d_nodes, &m.cap_nodes, dev_nodes, &err_);
       if (rc != RT2_OK) return rc;
       RT2_CUDA(cudaStreamSynchronize(m.stream));  // dev_nodes is a temporary
     }
@@ -830,11 +890,11 @@ int Renderer::UploadScene(const HostScene& scene) {
       offsets.push_back(static_cast<uint32_t>(refs.size()));
     }
     if (ok && !refs.empty() && refs.size() <= flat_max) {
-      rc = UploadBuf(&m.d_flat_refs, &m.cap_flat_refs, refs, m.stream, &err_);
+      rc = UploadBuf(m, &m.d_flat_refs, &m.cap_flat_refs, refs, &err_);
       if (rc != RT2_OK) return rc;
-      rc = UploadBuf(&m.d_flat_offsets, &m.cap_flat_offsets, offsets, m.stream, &err_);
+      rc = UploadBuf(m, &m.d_flat_offsets, &m.cap_flat_offsets, offsets, &err_);
       if (rc != RT2_OK) return rc;
-      rc = UploadBuf(&m.d_flat_bounds, &m.cap_flat_bounds, bounds, m.stream, &err_);
+      rc = UploadBuf(m, &m.d_flat_bounds, &m.cap_flat_bounds, bounds, &err_);
       if (rc != RT2_OK) return rc;
       RT2_CUDA(cudaStreamSynchronize(m.stream));  // the host vectors are temporaries
       d.flat_refs = static_cast<const uint32_t*>(m.d_flat_refs);
@@ -844,6 +904,7 @@ int Renderer::UploadScene(const HostScene& scene) {
     }
   }
   cam_params_ = scene.cam;
+  RT2_CUDA(cudaStreamSynchronize(m.stream));  // the staging arena (and any temporary above) may be reused from here on
   return RT2_OK;
 }
 
@@ -882,9 +943,9 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
     return RT2_ERR_UNSUPPORTED;
   }
   int rc;
-  rc = UploadBuf(&m.d_instances, &m.cap_instances, instances, m.stream, &err_);
+  rc = UploadBuf(m, &m.d_instances, &m.cap_instances, instances, &err_);
   if (rc != RT2_OK) return rc;
-  rc = UploadBuf(&m.d_media, &m.cap_media, media, m.stream, &err_);
+  rc = UploadBuf(m, &m.d_media, &m.cap_media, media, &err_);
   if (rc != RT2_OK) return rc;
   auto ensure = [&](void** ptr, size_t* cap, size_t bytes) -> int {
     if (bytes > *cap || *ptr == nullptr) {
@@ -1118,8 +1179,8 @@ int Renderer::RenderBatch(uint32_t n_frames) {
     uint32_t* keys = (sort_next && !last) ? m.sort_keys[0] : nullptr;
     if (m.fused) {
       // finish + inline shade; only noise-textured materials go through the bins
-      if (exact && m.fs_blocks == 2) {
-        k_finish_shade<ExactMath, 2><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
+      if (exact && m.fs_blocks == 3) {
+        k_finish_shade<ExactMath, 3><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
                                                                              m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
                                                                              m.ray_d[out], m.state[out], keys, m.radiance);
       } else if (exact) {
@@ -1231,7 +1292,16 @@ int Renderer::ReadMean(float* dst) {
   // accum / frame_idx_ — with no frames the reference divides by zero (NaN); we do the same
   k_resolve<<<m.grid_stream, kBlock, 0, m.stream>>>(P, static_cast<float>(frame_idx_), m.accum, m.mean_rgb, nullptr);
   launches_++;
-  RT2_CUDA(cudaMemcpyAsync(dst, m.mean_rgb, static_cast<size_t>(P) * 3 * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
+  const size_t bytes = static_cast<size_t>(P) * 3 * sizeof(float);
+  int rc = EnsureStage(m, bytes, &err_);
+  if (rc != RT2_OK) return rc;
+  if (m.h_stage_cap >= bytes) {  // D2H into page-locked memory, then a host copy into the caller's buffer
+    RT2_CUDA(cudaMemcpyAsync(m.h_stage, m.mean_rgb, bytes, cudaMemcpyDeviceToHost, m.stream));
+    rc = Synchronize();
+    if (rc == RT2_OK) std::memcpy(dst, m.h_stage, bytes);
+    return rc;
+  }
+  RT2_CUDA(cudaMemcpyAsync(dst, m.mean_rgb, bytes, cudaMemcpyDeviceToHost, m.stream));
   return Synchronize();
 }
 
@@ -1241,7 +1311,16 @@ int Renderer::ReadRGBA8(uint8_t* dst) {
   const uint32_t P = static_cast<uint32_t>(width_) * height_;
   k_resolve<<<m.grid_stream, kBlock, 0, m.stream>>>(P, static_cast<float>(frame_idx_), m.accum, nullptr, m.rgba8);
   launches_++;
-  RT2_CUDA(cudaMemcpyAsync(dst, m.rgba8, static_cast<size_t>(P) * 4, cudaMemcpyDeviceToHost, m.stream));
+  const size_t bytes = static_cast<size_t>(P) * 4;
+  int rc = EnsureStage(m, bytes, &err_);
+  if (rc != RT2_OK) return rc;
+  if (m.h_stage_cap >= bytes) {
+    RT2_CUDA(cudaMemcpyAsync(m.h_stage, m.rgba8, bytes, cudaMemcpyDeviceToHost, m.stream));
+    rc = Synchronize();
+    if (rc == RT2_OK) std::memcpy(dst, m.h_stage, bytes);
+    return rc;
+  }
+  RT2_CUDA(cudaMemcpyAsync(dst, m.rgba8, bytes, cudaMemcpyDeviceToHost, m.stream));
   return Synchronize();
 }
 
@@ -1372,6 +1451,54 @@ int Renderer::GetStats(rt2_stats* out) {
   out->sphere_tests = t[3];
   out->quad_tests = t[4];
   out->instance_visits = t[5];
+  return RT2_OK;
+}
+
+// FP32 FMA peak of the device, measured: 8 independent FMA chains per thread, every SM fully occupied (the
+// roofline the instruction-bound kernels are reported against must be measured, not nominal).
+__global__ void __launch_bounds__(256) k_fma_peak(float* __restrict__ out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      x0 = fmaf(x0, a, b), x1 = fmaf(x1, a, b), x2 = fmaf(x2, a, b), x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b), x5 = fmaf(x5, a, b), x6 = fmaf(x6, a, b), x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+int MeasureFp32Peak(int device, double* tflops, std::string* err) {
+  auto fail = [&](const char* what, cudaError_t e) {
+    *err = std::string(what) + " failed: " + cudaGetErrorString(e);
+    return RT2_ERR_CUDA;
+  };
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+  float* d = nullptr;
+  if ((e = cudaMalloc(&d, static_cast<size_t>(blocks) * 256 * sizeof(float))) != cudaSuccess) return fail("cudaMalloc", e);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(a);
+    k_fma_peak<<<blocks, 256>>>(d, iters, 0.999f, 0.001f);
+    cudaEventRecord(b);
+    if ((e = cudaEventSynchronize(b)) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double flops = 2.0 * 8 * 16 * static_cast<double>(iters) * blocks * 256;
+    if (ms > 0 && flops / (ms * 1e-3) * 1e-12 > best) best = flops / (ms * 1e-3) * 1e-12;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail("k_fma_peak", e);
+  *tflops = best;
   return RT2_OK;
 }
 

@@ -66,5 +66,6 @@ class Renderer {
 };
 
 int DeviceCount();
+int MeasureFp32Peak(int device, double* tflops, std::string* err);
 
 }  // namespace rt2

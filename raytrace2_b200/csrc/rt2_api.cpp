@@ -35,6 +35,12 @@ extern "C" {
 const char* rt2_last_error(void) { return g_last_error.c_str(); }
 int rt2_abi_version(void) { return RT2_ABI_VERSION; }
 int rt2_device_count(void) { return rt2::DeviceCount(); }
+int rt2_measure_fp32_peak(int32_t device, double* tflops) {
+  if (!tflops) return Fail(RT2_ERR_INVALID_ARG, "null argument");
+  std::string err;
+  int rc = rt2::MeasureFp32Peak(device, tflops, &err);
+  return rc == RT2_OK ? RT2_OK : Fail(rc, err);
+}
 
 // ---- scene -----------------------------------------------------------------------------------------------------
 int rt2_scene_load(const char* json_path, const char* data_dir, uint64_t perlin_seed, rt2_scene** out) {
