@@ -538,7 +538,6 @@ struct Renderer::Impl {
   uint32_t* sort_hist{nullptr};
   uint32_t* sort_bin_base{nullptr};
   int grid_sort{0};
-  int trav_variant{0};
   int fs_blocks{4};  // resident blocks per SM the fused kernel is compiled for (4: 64 registers, a few spills; measured +1-2 %)
   int trav_max_steps{8};  // node steps per round of the while-while traversal (measured: +12 % on the 1M-sphere scene, +1 % on book 2)
   int trav_fetch_threshold{kFetchThreshold};
@@ -615,21 +614,11 @@ int Renderer::Init(const HostScene& scene, const rt2_config& cfg) {
   if (cfg_.frame_stride < 1) cfg_.frame_stride = 1;
   // persistent grids: resident blocks per SM x SM count
   int occ = 0;
-  if (const char* e = getenv("RT2_TRAV_VAR")) m.trav_variant = atoi(e);
   if (const char* e = getenv("RT2_FS_BLOCKS")) m.fs_blocks = atoi(e);
   if (const char* e = getenv("RT2_TRAV_STEPS")) m.trav_max_steps = atoi(e);
   if (const char* e = getenv("RT2_TRAV_FETCH")) m.trav_fetch_threshold = atoi(e);
-  if (const char* e = getenv("RT2_L1_CARVEOUT")) {
-    const int c = atoi(e);  // percent of the unified L1/shared array reserved for shared memory
-    cudaFuncSetAttribute(k_traverse<ExactMath, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-    cudaFuncSetAttribute(k_traverse<ExactMath, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-    cudaFuncSetAttribute(k_traverse<ExactMath, false, 0, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-    cudaFuncSetAttribute(k_traverse<ExactMath, false, 1, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  }
   if (cfg_.flags & RT2_FLAG_FAST_MATH) {
     RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<FastMath, false>, kBlock, 0));
-  } else if (m.trav_variant >= 2) {
-    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false, 0, 5>, kBlock, 0));
   } else {
     RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false>, kBlock, 0));
   }
@@ -1166,9 +1155,6 @@ int Renderer::RenderBatch(uint32_t n_frames) {
       else k_traverse_flat<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, 0u, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav);
     } else if (exact) {
       if (profiling_) k_traverse<ExactMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
-      else if (m.trav_variant == 1) k_traverse<ExactMath, false, 1><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
-      else if (m.trav_variant == 2) k_traverse<ExactMath, false, 0, 5><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
-      else if (m.trav_variant == 3) k_traverse<ExactMath, false, 1, 5><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
       else k_traverse<ExactMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
     } else {
       if (profiling_) k_traverse<FastMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
