@@ -273,6 +273,10 @@ int rt2_read_mean_rgb32f(rt2_renderer* r, float* dst);
 int rt2_read_rgba8(rt2_renderer* r, uint8_t* dst);
 /* Raw accumulators: sum (W*H*3 floats) and, with RT2_FLAG_MOMENTS, sum of squares (else sumsq may be NULL). */
 int rt2_read_accum(rt2_renderer* r, float* sum, float* sumsq);
+/* Checkpoint / resume (the reference has none: a 10k-spp render that dies starts over): restore the accumulators read with
+ * rt2_read_accum and the number of frames they hold.  Frames rendered afterwards continue the same stratification and Philox
+ * counters, so an interrupted + resumed render is bit-identical with an uninterrupted one (same batch partition). */
+int rt2_write_accum(rt2_renderer* r, const float* sum, const float* sumsq, uint64_t frames);
 /* Device pointer of the W*H*4-float accumulator (rgb + pad) for an external reduce (NCCL / torch.distributed). */
 int rt2_accum_device_ptr(rt2_renderer* r, void** ptr, size_t* n_floats);
 /* After an external reduce: declare how many frames the accumulator now holds in total. */

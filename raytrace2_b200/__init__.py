@@ -6,6 +6,7 @@ Pixels / NonConvertedPixels / FrameIdx / Dims; ``SceneLoader.LoadScene``; ``Writ
 """
 from ._capi import (LIB_PATH, RT2_FLAG_FAST_MATH, RT2_FLAG_GPU_LBVH, RT2_FLAG_MOMENTS, RT2_FLAG_NO_FUSED_SHADE, RT2_FLAG_SORT_RAYS, Rt2Error, load_library)
 from .raytracer import RayTracer, Scene, SceneLoader, WriteImage, run_app
+from . import scene_builder
 from .distributed import DistributedRayTracer, frame_partition
 
 __all__ = ["LIB_PATH", "RT2_FLAG_FAST_MATH", "RT2_FLAG_GPU_LBVH", "RT2_FLAG_MOMENTS", "RT2_FLAG_NO_FUSED_SHADE", "RT2_FLAG_SORT_RAYS", "Rt2Error", "load_library",

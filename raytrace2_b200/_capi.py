@@ -137,6 +137,7 @@ PROTOTYPES = {
     "rt2_read_mean_rgb32f": (C.c_int, [_P, _P]),
     "rt2_read_rgba8": (C.c_int, [_P, _P]),
     "rt2_read_accum": (C.c_int, [_P, _P, _P]),
+    "rt2_write_accum": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "rt2_accum_device_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "rt2_set_frame_idx": (C.c_int, [_P, C.c_uint64]),
     "rt2_intersect": (C.c_int, [_P, _P, C.c_size_t, C.c_float, C.c_float, C.c_int, _P]),

@@ -1341,6 +1341,37 @@ int Renderer::ReadAccum(float* sum, float* sumsq) {
   return RT2_OK;
 }
 
+// Restores the accumulators (checkpoint / resume): sum / sumsq as W*H*3 floats, `frames` = samples they hold.
+int Renderer::WriteAccum(const float* sum, const float* sumsq, uint64_t frames) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  int rc = Synchronize();
+  if (rc != RT2_OK) return rc;
+  const size_t P = static_cast<size_t>(width_) * height_;
+  std::vector<float4> tmp(P);
+  auto put = [&](const float* src, float4* dst) -> int {
+    for (size_t i = 0; i < P; i++) tmp[i] = make_float4(src[3 * i + 0], src[3 * i + 1], src[3 * i + 2], 0.0f);
+    RT2_CUDA(cudaMemcpy(dst, tmp.data(), P * sizeof(float4), cudaMemcpyHostToDevice));
+    return RT2_OK;
+  };
+  if (!sum) {
+    err_ = "null sum";
+    return RT2_ERR_INVALID_ARG;
+  }
+  rc = put(sum, m.accum);
+  if (rc != RT2_OK) return rc;
+  if (sumsq) {
+    if (!m.accum_sq) {
+      err_ = "renderer was created without RT2_FLAG_MOMENTS";
+      return RT2_ERR_STATE;
+    }
+    rc = put(sumsq, m.accum_sq);
+    if (rc != RT2_OK) return rc;
+  }
+  frame_idx_ = frames;
+  return RT2_OK;
+}
+
 int Renderer::AccumDevicePtr(void** ptr, size_t* n_floats) {
   *ptr = impl_->accum;
   *n_floats = static_cast<size_t>(width_) * height_ * 4;

@@ -26,6 +26,7 @@ class Renderer {
   int ReadMean(float* dst);          // RayTracer::NonConvertedPixels
   int ReadRGBA8(uint8_t* dst);       // RayTracer::Pixels
   int ReadAccum(float* sum, float* sumsq);
+  int WriteAccum(const float* sum, const float* sumsq, uint64_t frames);
   int AccumDevicePtr(void** ptr, size_t* n_floats);
   int Intersect(const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out);
   int GetStats(rt2_stats* out);

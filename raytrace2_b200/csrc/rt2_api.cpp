@@ -203,6 +203,9 @@ int rt2_read_rgba8(rt2_renderer* r, uint8_t* dst) {
   RT2_FORWARD(r->impl.ReadRGBA8(dst))
 }
 int rt2_read_accum(rt2_renderer* r, float* sum, float* sumsq) { RT2_FORWARD(r->impl.ReadAccum(sum, sumsq)) }
+int rt2_write_accum(rt2_renderer* r, const float* sum, const float* sumsq, uint64_t frames) {
+  RT2_FORWARD(r->impl.WriteAccum(sum, sumsq, frames))
+}
 int rt2_accum_device_ptr(rt2_renderer* r, void** ptr, size_t* n_floats) {
   if (!ptr || !n_floats) return Fail(RT2_ERR_INVALID_ARG, "null argument");
   RT2_FORWARD(r->impl.AccumDevicePtr(ptr, n_floats))

@@ -47,6 +47,11 @@ class Scene:
         return cls(h.value)
 
     @classmethod
+    def from_builder(cls, builder, data_dir: Optional[str] = None, perlin_seed: int = 0) -> "Scene":
+        """Compiles a :class:`raytrace2_b200.scene_builder.SceneBuilder` document."""
+        return cls.from_string(builder.to_json(), data_dir, perlin_seed)
+
+    @classmethod
     def from_string(cls, text: str, data_dir: Optional[str] = None, perlin_seed: int = 0) -> "Scene":
         lib = load_library()
         h = C.c_void_p()
@@ -239,6 +244,40 @@ class RayTracer:
         ss = np.empty((h, w, 3), np.float32) if moments else None
         check(self._lib.rt2_read_accum(self._h, s.ctypes.data_as(C.c_void_p), ss.ctypes.data_as(C.c_void_p) if moments else None))
         return (s, ss) if moments else s
+
+    def write_accum(self, s: np.ndarray, ss: Optional[np.ndarray], frames: int) -> None:
+        s = np.ascontiguousarray(s, np.float32)
+        ss = None if ss is None else np.ascontiguousarray(ss, np.float32)
+        check(self._lib.rt2_write_accum(self._h, s.ctypes.data_as(C.c_void_p), ss.ctypes.data_as(C.c_void_p) if ss is not None else None, frames))
+
+    def save_checkpoint(self, path: str) -> None:
+        """Accumulators + frame index + the settings a resume must match, as one .npz (the reference has no checkpointing:
+        SURVEY §5).  Resume with :meth:`load_checkpoint` on a renderer created with the same scene / seed / num_samples."""
+        moments = bool(self._cfg.flags & _capi.RT2_FLAG_MOMENTS)
+        acc = self.read_accum(moments=moments)
+        s, ss = acc if moments else (acc, None)
+        w, h = self.Dims()
+        np.savez(path, sum=s, sumsq=ss if ss is not None else np.zeros(0, np.float32), frames=np.uint64(self.FrameIdx()),
+                 dims=np.array([w, h], np.int32), seed=np.uint64(self._cfg.seed), num_samples=np.int32(self._cfg.samples_per_pixel),
+                 max_depth=np.int32(self._cfg.max_depth), frame_offset=np.int32(self._cfg.frame_offset), frame_stride=np.int32(self._cfg.frame_stride))
+
+    def load_checkpoint(self, path: str) -> int:
+        """Restores a checkpoint written by :meth:`save_checkpoint`; returns the number of frames it holds."""
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        w, h = self.Dims()
+        if tuple(int(x) for x in z["dims"]) != (w, h):
+            raise ValueError(f"checkpoint is {tuple(z['dims'])}, renderer is {(w, h)}")
+        for key, mine in (("seed", self._cfg.seed), ("num_samples", self._cfg.samples_per_pixel), ("max_depth", self._cfg.max_depth),
+                          ("frame_offset", self._cfg.frame_offset), ("frame_stride", max(1, self._cfg.frame_stride))):
+            theirs = int(z[key]) if key != "frame_stride" else max(1, int(z[key]))
+            if theirs != int(mine):
+                raise ValueError(f"checkpoint {key}={theirs} does not match the renderer's {int(mine)}")
+        ss = z["sumsq"] if z["sumsq"].size else None
+        if ss is not None and not (self._cfg.flags & _capi.RT2_FLAG_MOMENTS):
+            ss = None
+        frames = int(z["frames"])
+        self.write_accum(z["sum"], ss, frames)
+        return frames
 
     def accum_device_ptr(self) -> Tuple[int, int]:
         p, n = C.c_void_p(), C.c_size_t()
