@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define RT2_ABI_VERSION 1
+#define RT2_ABI_VERSION 2
 
 enum {
   RT2_OK = 0,
@@ -43,8 +43,10 @@ enum {
 /* material types (Material.hpp:31-65); RT2_MAT_TEXTURE is the reference's "MaterialTexture" (textured lambertian) */
 enum { RT2_MAT_LAMBERTIAN = 0, RT2_MAT_METAL = 1, RT2_MAT_DIELECTRIC = 2, RT2_MAT_TEXTURE = 3, RT2_MAT_DIFFUSE_LIGHT = 4,
        RT2_MAT_ISOTROPIC = 5, RT2_MAT_INVALID = 6 };
-/* texture types (Texture.hpp:14-36) */
-enum { RT2_TEX_SOLID = 0, RT2_TEX_CHECKER = 1, RT2_TEX_NOISE = 2, RT2_TEX_INVALID = 3 };
+/* texture types (Texture.hpp:14-36).  RT2_TEX_IMAGE is a schema extension ({"type": "image", "path": ...}):
+ * the reference carries (u, v) through Texture::Value (Texture.hpp:15, Sphere.cpp:34,39-43, Quad.cpp:15) but has no texture
+ * that reads them; the lookup follows the book the reference implements (nearest texel, v flipped, clamped). */
+enum { RT2_TEX_SOLID = 0, RT2_TEX_CHECKER = 1, RT2_TEX_NOISE = 2, RT2_TEX_IMAGE = 3, RT2_TEX_INVALID = 4 };
 
 /* Sphere.hpp:14-34 — centre(time) = center0 + time * displacement */
 typedef struct rt2_sphere {
@@ -113,8 +115,16 @@ typedef struct rt2_texture {
   float albedo[3];       /* solid colour / noise albedo */
   float scale;           /* checker: inv_scale (= 1.f / scale, Texture.hpp:21); noise: scale */
   uint32_t noise_type;   /* 0 = perlin, 1 = marble (Texture.hpp:30) */
-  uint32_t pad[3];
+  uint32_t image_idx;    /* image: index into the image table */
+  uint32_t pad[2];
 } rt2_texture; /* 48 B */
+
+/* One decoded image: texels are linear-light RGBA float32, row 0 = top of the picture, stored in one shared array. */
+typedef struct rt2_image {
+  uint32_t texel_offset; /* first texel (in float4 units) */
+  uint32_t width, height;
+  uint32_t pad;
+} rt2_image; /* 16 B */
 
 /* PerlinNoiseGen.hpp:15-20; the hash mask is 255 regardless of point_count (PerlinNoiseGen.cpp:83), so tables are
  * stored with 256 entries (entries >= point_count are never produced by a valid permutation and are zero). */
@@ -167,6 +177,10 @@ typedef struct rt2_scene_desc {
   float min_inv_scale; /* smallest singular value over all instance chains' inverse 3x3 (1 for rigid chains) */
   int32_t width, height; /* scene-authored dims, or 1600x900 (App.cpp:115,122-125) */
   rt2_camera camera;     /* computed for (width, height) */
+  uint32_t n_images;
+  uint32_t n_image_texels;   /* float4 texels over all images */
+  const rt2_image* images;
+  const float* image_texels; /* 4 * n_image_texels floats */
 } rt2_scene_desc;
 
 /* ---- scene: replaces serialize::SceneLoader::LoadScene (src/Serialize.hpp:21-22, Serialize.cpp:199-360) plus the
@@ -248,7 +262,7 @@ typedef struct rt2_hit {
   uint32_t prim;       /* RT2 prim ref of the closest leaf (RT2_PRIM_NONE on miss) */
   int32_t instance;    /* flattened instance index or -1 */
   uint32_t front_face; /* 0/1 */
-  uint32_t pad;
+  uint32_t uv16;       /* HitRecord::uv (Sphere.cpp:34, Quad.cpp:15) as two 16-bit unorms, u | v << 16; 0 for media and misses */
 } rt2_hit; /* 48 B */
 
 /* Uploads the flattened scene to `cfg->device` and allocates the wavefront state. ≡ RayTracer + OnResize. */

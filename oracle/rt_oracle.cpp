@@ -206,6 +206,7 @@ struct AABB {
 };
 struct HitRecord {
   V3 point, normal;
+  real u{0}, v{0};  // HitRecord::uv (HitRecord.hpp:12): set by Sphere::Hit / Quad::IsInterior, read only by image textures
   real t{0};
   int material{-1};
   bool front_face{false};
@@ -251,7 +252,14 @@ struct Sphere : Hittable {
     rec.point = r.At(root);
     rec.material = material;
     rec.leaf_id = leaf_id;
-    rec.SetFaceNormal(r, (rec.point - cc) / radius);
+    V3 outward = (rec.point - cc) / radius;
+    rec.SetFaceNormal(r, outward);
+    {  // rec.uv = GetUV(outward_normal) (Sphere.cpp:34,39-43)
+      const real pi = 3.14159265358979323846f;
+      real theta = std::acos(-outward.y), phi = std::atan2(-outward.z, outward.x) + pi;
+      rec.u = phi / (2.f * pi);
+      rec.v = theta / pi;
+    }
     return true;
   }
   AABB Box() const override { return box; }
@@ -282,6 +290,7 @@ struct Quad : Hittable {
     if (!unit.Contains(alpha) || !unit.Contains(beta)) return false;
     rec.t = tt;
     rec.point = p;
+    rec.u = alpha, rec.v = beta;  // Quad.cpp:15
     rec.material = material;
     rec.leaf_id = leaf_id;
     rec.SetFaceNormal(r, normal);
@@ -444,7 +453,9 @@ struct Perlin {
   }
 };
 struct Texture {
-  int type{0};  // 0 solid, 1 checker, 2 noise
+  int type{0};  // 0 solid, 1 checker, 2 noise, 3 image (schema extension: nearest texel of a linear RGB image, v flipped)
+  int img_w{0}, img_h{0};
+  std::vector<float> texels;  // 3 floats per texel, row 0 = top
   V3 albedo{1, 1, 1};
   real scale{1};  // checker: inv_scale
   int even{0}, odd{0}, noise_type{1};
@@ -507,11 +518,19 @@ struct Scene {
   int next_leaf{0};
 };
 
-static V3 TexValue(const Scene& s, int idx, V3 p) {  // Texture.hpp:14-17, Texture.cpp:7-22
+static V3 TexValue(const Scene& s, int idx, V3 p, real u = 0, real v = 0) {  // Texture.hpp:14-17, Texture.cpp:7-22
   const Texture& t = s.textures[idx];
+  if (t.type == 3) {  // image_texture::value of the book the reference follows (no counterpart in the reference itself)
+    if (t.img_h <= 0) return V3{0, 1, 1};
+    u = std::fmin(std::fmax(u, real(0)), real(1));
+    v = 1.0f - std::fmin(std::fmax(v, real(0)), real(1));
+    int i = std::min(static_cast<int>(u * t.img_w), t.img_w - 1), j = std::min(static_cast<int>(v * t.img_h), t.img_h - 1);
+    const float* c = &t.texels[(static_cast<size_t>(j) * t.img_w + i) * 3];
+    return V3{c[0], c[1], c[2]};
+  }
   if (t.type == 1) {
     int ix = static_cast<int>(std::floor(t.scale * p.x)), iy = static_cast<int>(std::floor(t.scale * p.y)), iz = static_cast<int>(std::floor(t.scale * p.z));
-    return TexValue(s, (ix + iy + iz) % 2 == 0 ? t.even : t.odd, p);
+    return TexValue(s, (ix + iy + iz) % 2 == 0 ? t.even : t.odd, p, u, v);
   }
   if (t.type == 2) {
     if (t.noise_type == 0) return t.albedo * real(0.5) * (1.0f + t.perlin.Noise(t.scale * p));
@@ -528,7 +547,7 @@ static bool Scatter(const Scene& s, const Material& m, const Ray& in, const HitR
       V3 d = rec.normal + RandUnitVec3();
       if (NearZero(d)) d = rec.normal;
       out = Ray{rec.point, d, in.time};
-      att = (m.type == 0) ? m.albedo : TexValue(s, m.tex, rec.point);
+      att = (m.type == 0) ? m.albedo : TexValue(s, m.tex, rec.point, rec.u, rec.v);
       return true;
     }
     case 1: {
@@ -554,7 +573,7 @@ static bool Scatter(const Scene& s, const Material& m, const Ray& in, const HitR
     }
     case 5: {
       out = Ray{rec.point, RandUnitVec3(), in.time};
-      att = TexValue(s, m.tex, rec.point);
+      att = TexValue(s, m.tex, rec.point, rec.u, rec.v);
       return true;
     }
     default: return false;
@@ -569,7 +588,7 @@ static V3 RayColor(const Ray& r, int depth, const Scene& s) {
   tl_rays++;
   if (!s.root->Hit(s, r, Interval{0.001f, kInf}, rec)) return s.background;
   const Material& m = s.materials[rec.material];
-  V3 emit = (m.type == 4) ? TexValue(s, m.tex, rec.point) : V3{0, 0, 0};
+  V3 emit = (m.type == 4) ? TexValue(s, m.tex, rec.point, rec.u, rec.v) : V3{0, 0, 0};
   V3 att;
   Ray out;
   if (Scatter(s, m, r, rec, att, out)) return att * RayColor(out, depth - 1, s) + emit;
@@ -710,6 +729,36 @@ int orc_perlin_set(void* h, int tex, const int32_t* px, const int32_t* py, const
     p.vec[i] = V3{vec[i * 3], vec[i * 3 + 1], vec[i * 3 + 2]};
   }
   return p.count;
+}
+// Image texture (schema extension): rgb = 3 floats per texel, already linear, row 0 = top.
+int orc_add_image_texture(void* h, int w, int ht, const float* rgb) {
+  auto* s = static_cast<Scene*>(h);
+  Texture t;
+  t.type = 3;
+  t.img_w = w, t.img_h = ht;
+  t.texels.assign(rgb, rgb + static_cast<size_t>(w) * ht * 3);
+  s->textures.push_back(std::move(t));
+  return static_cast<int>(s->textures.size() - 1);
+}
+void orc_texture_value_uv(void* h, int tex, const float* pts, const float* uv, size_t n, float* rgb) {
+  auto* s = static_cast<Scene*>(h);
+  for (size_t i = 0; i < n; i++) {
+    V3 c = TexValue(*s, tex, V3{pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]}, uv[i * 2], uv[i * 2 + 1]);
+    for (int k = 0; k < 3; k++) rgb[i * 3 + k] = c[k];
+  }
+}
+// orc_intersect + HitRecord::uv
+void orc_intersect_uv(void* h, const float* rays, size_t n, float tmin, float tmax, uint8_t* hit, float* uv) {
+  auto* s = static_cast<Scene*>(h);
+  for (size_t i = 0; i < n; i++) {
+    const float* r = rays + i * 7;
+    Ray ray{V3{r[0], r[1], r[2]}, V3{r[3], r[4], r[5]}, r[6]};
+    HitRecord rec;
+    bool got = s->root->Hit(*s, ray, Interval{tmin, tmax}, rec);
+    hit[i] = got;
+    uv[i * 2] = got ? rec.u : 0;
+    uv[i * 2 + 1] = got ? rec.v : 0;
+  }
 }
 void orc_texture_value(void* h, int tex, const float* pts, size_t n, float* rgb) {
   auto* s = static_cast<Scene*>(h);

@@ -52,6 +52,9 @@ def lib() -> C.CDLL:
         L.orc_perlin_get.argtypes = [P, C.c_int, P, P, P, P]
         L.orc_perlin_set.argtypes = [P, C.c_int, P, P, P, P]
         L.orc_texture_value.argtypes = [P, C.c_int, P, C.c_size_t, P]
+        L.orc_add_image_texture.argtypes = [P, C.c_int, C.c_int, P]
+        L.orc_texture_value_uv.argtypes = [P, C.c_int, P, P, C.c_size_t, P]
+        L.orc_intersect_uv.argtypes = [P, P, C.c_size_t, C.c_float, C.c_float, P, P]
         L.orc_intersect.argtypes = [P, P, C.c_size_t, C.c_float, C.c_float] + [P] * 7
         L.orc_render.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         _lib = L
@@ -80,6 +83,18 @@ def _int_default(obj, key, default):
 
 
 MAT = {"lambertian": 0, "metal": 1, "dielectric": 2, "texture": 3, "diffuse_light": 4, "isotropic": 5}
+
+
+def _load_image_linear(path):
+    """[H, W, 3] float32, linear light, row 0 = top; a missing file is the book's 1x1 cyan debugging texture."""
+    try:
+        from PIL import Image
+        with Image.open(path) as im:
+            a = np.asarray(im.convert("RGB"), np.uint8)
+    except Exception:
+        return np.array([[[0.0, 1.0, 1.0]]], np.float32)
+    lut = (np.arange(256, dtype=np.float32) / np.float32(255.0)) ** np.float32(2.2)
+    return np.ascontiguousarray(lut[a].astype(np.float32))
 
 
 class PortScene:
@@ -139,6 +154,11 @@ class PortScene:
                 elif ty == "noise":
                     add_tex(2, _arr(t, "albedo", [1, 1, 1]), float(np.float32(t.get("scale", 1.0))),
                             noise_type=_int_default(t, "noise_type", 1), point_count=_int_default(t, "point_count", 256))
+                elif ty == "image":
+                    # schema extension: decoded with PIL (independent of the product's decoder), bytes -> linear by the 2.2 power law
+                    rgb = _load_image_linear(os.path.join(data_dir, t.get("path", "")))
+                    idx = L.orc_add_image_texture(h, rgb.shape[1], rgb.shape[0], _p(rgb))
+                    self.n_textures = idx + 1
                 else:
                     add_tex(0, [0, 0, 0])
         legacy = isinstance(doc.get("primitives"), dict)
@@ -312,6 +332,26 @@ class PortScene:
         px, py, pz = (np.ascontiguousarray(a, np.int32) for a in (px, py, pz))
         vec = np.ascontiguousarray(vec, np.float32)
         return self.L.orc_perlin_set(self.h, tex_idx, _p(px), _p(py), _p(pz), _p(vec))
+
+    def texture_value_uv(self, tex_idx: int, pts, uv):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros_like(pts)
+        self.L.orc_texture_value_uv(self.h, tex_idx, _p(pts), _p(uv), pts.shape[0], _p(out))
+        return out
+
+    def intersect_uv(self, origins, directions, times=None, tmin=0.001, tmax=3.402823466e+38):
+        """(hit flags, HitRecord::uv) of the closest hit — Sphere.cpp:34,39-43 / Quad.cpp:15."""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        rays = np.zeros((n, 7), np.float32)
+        rays[:, 0:3], rays[:, 3:6] = o, d
+        if times is not None:
+            rays[:, 6] = times
+        hit, uv = np.zeros(n, np.uint8), np.zeros((n, 2), np.float32)
+        self.L.orc_intersect_uv(self.h, _p(rays), n, tmin, tmax, _p(hit), _p(uv))
+        return hit, uv
 
     def texture_value(self, tex_idx: int, pts):
         pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)

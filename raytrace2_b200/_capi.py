@@ -63,7 +63,11 @@ class Material(C.Structure):
 
 class Texture(C.Structure):
     _fields_ = [("type", C.c_uint32), ("even_tex_idx", C.c_uint32), ("odd_tex_idx", C.c_uint32), ("perlin_idx", C.c_uint32),
-                ("albedo", C.c_float * 3), ("scale", C.c_float), ("noise_type", C.c_uint32), ("pad", C.c_uint32 * 3)]
+                ("albedo", C.c_float * 3), ("scale", C.c_float), ("noise_type", C.c_uint32), ("image_idx", C.c_uint32), ("pad", C.c_uint32 * 2)]
+
+
+class Image(C.Structure):
+    _fields_ = [("texel_offset", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("pad", C.c_uint32)]
 
 
 class Perlin(C.Structure):
@@ -92,6 +96,7 @@ class SceneDesc(C.Structure):
         ("nodes", C.POINTER(BvhNode)),
         ("background", C.c_float * 3), ("min_inv_scale", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
         ("camera", Camera),
+        ("n_images", C.c_uint32), ("n_image_texels", C.c_uint32), ("images", C.POINTER(Image)), ("image_texels", C.POINTER(C.c_float)),
     ]
 
 
@@ -110,7 +115,7 @@ class Stats(C.Structure):
 
 class Hit(C.Structure):
     _fields_ = [("point", C.c_float * 3), ("t", C.c_float), ("normal", C.c_float * 3), ("material", C.c_int32),
-                ("prim", C.c_uint32), ("instance", C.c_int32), ("front_face", C.c_uint32), ("pad", C.c_uint32)]
+                ("prim", C.c_uint32), ("instance", C.c_int32), ("front_face", C.c_uint32), ("uv16", C.c_uint32)]
 
 
 # every symbol include/rt2.h declares: name -> (restype, argtypes)

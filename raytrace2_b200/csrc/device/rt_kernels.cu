@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kBlock) k_finish_hit(const DeviceScene S, cons
     HitOut h;
     finish_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, bounce,
                   false, h);
-    hit0[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t);
+    hit0[i] = make_float4(h.p.x, h.p.y, h.p.z, __uint_as_float(pack_uv16(h.u, h.v)));  // .w: (u, v); t is not needed downstream
     const uint32_t mbits = (h.material < 0) ? 0xFFFFFFFFu : (static_cast<uint32_t>(h.material) | (h.front_face ? 0x80000000u : 0u));
     hit1[i] = make_float4(h.n.x, h.n.y, h.n.z, __uint_as_float(mbits));
     bin_push(counters, bins.base, bins.stride, bin_of_material(S, h.material), i);
@@ -235,11 +235,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
         const uint32_t type = __float_as_uint(m0.x);
         if (__float_as_uint(m1.w) != 0u) {
           // deferred (noise-textured): record + bin, shaded by the per-bin kernels
-          hit0[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t);
+          hit0[i] = make_float4(h.p.x, h.p.y, h.p.z, __uint_as_float(pack_uv16(h.u, h.v)));
           hit1[i] = make_float4(h.n.x, h.n.y, h.n.z, __uint_as_float(static_cast<uint32_t>(h.material) | (h.front_face ? 0x80000000u : 0u)));
           bin_push(counters, bins.base, bins.stride, bin_of_material(S, h.material), i);
         } else if (type == RT2_MAT_DIFFUSE_LIGHT) {
-          const F3 c = texture_value_simple(S, __float_as_uint(m0.y), h.p);  // DiffuseLight::Emit (Material.cpp:71-74)
+          const F3 c = texture_value_simple(S, __float_as_uint(m0.y), h.p, h.u, h.v);  // DiffuseLight::Emit (Material.cpp:71-74)
           radiance[slot] = make_float4(st.x * c.x, st.y * c.y, st.z * c.z, 0.0f);
         } else if (emit_next) {
           const uint4 r = rng_draw(key, bounce, kStreamScatter);
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
             const F3 u = unit_vector(u01(r.x), u01(r.y));
             dir = {h.n.x + u.x, h.n.y + u.y, h.n.z + u.z};
             if (near_zero(dir)) dir = h.n;
-            att = (type == RT2_MAT_LAMBERTIAN) ? F3{m1.x, m1.y, m1.z} : texture_value_simple(S, __float_as_uint(m0.y), h.p);
+            att = (type == RT2_MAT_LAMBERTIAN) ? F3{m1.x, m1.y, m1.z} : texture_value_simple(S, __float_as_uint(m0.y), h.p, h.u, h.v);
             cls = (type == RT2_MAT_LAMBERTIAN) ? 0 : 1;
           } else if (type == RT2_MAT_METAL) {
             att = scatter<RT2_MAT_METAL>(S, m0, m1, make_f3(d), h.p, h.n, h.front_face, r, dir);
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
           } else {  // RT2_MAT_ISOTROPIC, Material.cpp:76-83
             cls = 4;
             dir = unit_vector(u01(r.x), u01(r.y));
-            att = texture_value_simple(S, __float_as_uint(m0.y), h.p);
+            att = texture_value_simple(S, __float_as_uint(m0.y), h.p, h.u, h.v);
           }
           emit = true;
           no = make_float4(h.p.x, h.p.y, h.p.z, o.w);
@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(kBlock) k_shade_terminal(const DeviceScene S, 
     } else {
       const float4 h0 = hit0[i];
       const float4 m0 = __ldg(S.materials + 2 * (mbits & 0x7FFFFFFFu));
-      c = texture_value(S, __float_as_uint(m0.y), make_f3(h0));  // DiffuseLight::Emit (Material.cpp:71-74)
+      const float2 uv = unpack_uv16(__float_as_uint(h0.w));
+      c = texture_value(S, __float_as_uint(m0.y), make_f3(h0), uv.x, uv.y);  // DiffuseLight::Emit (Material.cpp:71-74)
     }
     radiance[__float_as_uint(st.w)] = make_float4(st.x * c.x, st.y * c.y, st.z * c.z, 0.0f);
   }
@@ -369,7 +370,8 @@ __global__ void __launch_bounds__(kBlock) k_shade_scatter(const DeviceScene S, c
     const RngKey key = key_of_slot(fp, __float_as_uint(st.w));
     const uint4 r = rng_draw(key, bounce, kStreamScatter);
     F3 dir;
-    const F3 att = scatter<kType>(S, m0, m1, make_f3(d), make_f3(h0), make_f3(h1), (mbits >> 31) != 0u, r, dir);
+    const float2 uv = unpack_uv16(__float_as_uint(h0.w));
+    const F3 att = scatter<kType>(S, m0, m1, make_f3(d), make_f3(h0), make_f3(h1), (mbits >> 31) != 0u, r, dir, uv.x, uv.y);
     const uint32_t dst = base + j;
     out_o[dst] = make_float4(h0.x, h0.y, h0.z, time);
     out_d[dst] = make_float4(dir.x, dir.y, dir.z, 0.0f);
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(kBlock) k_finish_intersect(const DeviceScene S
   r.prim = (h.material < 0) ? RT2_PRIM_NONE : h.prim;
   r.instance = (h.material < 0) ? -1 : h.instance;
   r.front_face = h.front_face ? 1u : 0u;
-  r.pad = 0;
+  r.uv16 = (h.material < 0) ? 0u : pack_uv16(h.u, h.v);
   out[i] = r;
 }
 
@@ -494,6 +496,9 @@ struct Renderer::Impl {
   void* d_media{nullptr};
   void* d_media_bounds{nullptr};
   size_t cap_media_bounds{0};
+  void* d_images{nullptr};
+  void* d_image_texels{nullptr};
+  size_t cap_images{0}, cap_image_texels{0};
   void* d_flat_refs{nullptr};
   void* d_flat_offsets{nullptr};
   void* d_flat_bounds{nullptr};
@@ -558,7 +563,7 @@ Renderer::~Renderer() {
   cudaSetDevice(cfg_.device);
   FreeState();
   Impl& m = *impl_;
-  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_flat_bounds};
+  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_flat_bounds, m.d_images, m.d_image_texels};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.totals) cudaFree(m.totals);
@@ -707,7 +712,8 @@ int Renderer::UploadScene(const HostScene& scene) {
                    scene.instances.size() * sizeof(rt2_instance) + scene.media.size() * sizeof(rt2_medium) +
                    scene.materials.size() * sizeof(rt2_material) + scene.textures.size() * sizeof(rt2_texture) +
                    scene.perlin.size() * sizeof(rt2_perlin) + scene.prim_refs.size() * sizeof(uint32_t) +
-                   scene.nodes.size() * sizeof(rt2_bvh_node) + scene.media_bounds.size() * sizeof(float) +
+                   scene.nodes.size() * sizeof(rt2_bvh_node) + scene.media_bounds.size() * sizeof(float) + scene.images.size() * sizeof(rt2_image) +
+                   scene.image_texels.size() * sizeof(float) +
                    (kFlatMaxPrims + scene.instances.size() * 9 + 8) * sizeof(uint32_t) + 32 * 256;
     RT2_CUDA(cudaStreamSynchronize(m.stream));  // earlier copies out of the arena
     rc = EnsureStage(m, total, &err_);
@@ -758,6 +764,8 @@ int Renderer::UploadScene(const HostScene& scene) {
   UP(d_textures, textures, cap_textures)
   UP(d_perlin, perlin, cap_perlin)
   UP(d_media_bounds, media_bounds, cap_media_bounds)
+  UP(d_images, images, cap_images)
+  UP(d_image_texels, image_texels, cap_image_texels)
   if (!gpu_bvh) {
     UP(d_instances, instances, cap_instances)
     UP(d_media, media, cap_media)
@@ -799,6 +807,9 @@ int Renderer::UploadScene(const HostScene& scene) {
   d.instances = static_cast<const uint4*>(m.d_instances);
   d.media = static_cast<const uint4*>(m.d_media);
   d.media_bounds = static_cast<const float4*>(m.d_media_bounds);
+  d.images = static_cast<const uint4*>(m.d_images);
+  d.image_texels = static_cast<const float4*>(m.d_image_texels);
+  d.n_images = static_cast<uint32_t>(scene.images.size());
   d.materials = static_cast<const float4*>(m.d_materials);
   d.textures = static_cast<const float4*>(m.d_textures);
   d.perlin = static_cast<const rt2_perlin*>(m.d_perlin);

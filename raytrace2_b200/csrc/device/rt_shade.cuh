@@ -45,9 +45,30 @@ __device__ __forceinline__ float perlin_turb(const rt2_perlin* __restrict__ P, F
   return fabsf(accum);
 }
 
+// Image texture lookup (schema extension; the book's image_texture::value): u clamped to [0,1], v flipped and clamped,
+// nearest texel, texels already linear.
+__device__ __forceinline__ F3 image_value(const DeviceScene& S, uint32_t image_idx, float u, float v) {
+  const uint4 im = __ldg(S.images + image_idx);
+  u = fminf(fmaxf(u, 0.0f), 1.0f);
+  v = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+  const uint32_t i = min(static_cast<uint32_t>(u * static_cast<float>(im.y)), im.y - 1u);
+  const uint32_t j = min(static_cast<uint32_t>(v * static_cast<float>(im.z)), im.z - 1u);
+  const float4 c = __ldg(S.image_texels + im.x + static_cast<size_t>(j) * im.y + i);
+  return {c.x, c.y, c.z};
+}
+// (u, v) of a hit record travel through the queues as two 16-bit unorms
+__device__ __forceinline__ uint32_t pack_uv16(float u, float v) {
+  const uint32_t a = static_cast<uint32_t>(fminf(fmaxf(u, 0.0f), 1.0f) * 65535.0f + 0.5f);
+  const uint32_t b = static_cast<uint32_t>(fminf(fmaxf(v, 0.0f), 1.0f) * 65535.0f + 0.5f);
+  return a | (b << 16);
+}
+__device__ __forceinline__ float2 unpack_uv16(uint32_t w) {
+  return make_float2(static_cast<float>(w & 0xFFFFu) * (1.0f / 65535.0f), static_cast<float>(w >> 16) * (1.0f / 65535.0f));
+}
+
 // texture::{SolidColor,Checker,Noise}::Value (Texture.hpp:14-17, Texture.cpp:7-22).  Checker recursion through texture
 // indices is followed for at most 8 levels (the reference would recurse forever on a cycle).
-__device__ __forceinline__ F3 texture_value(const DeviceScene& S, uint32_t tex_idx, F3 p) {
+__device__ __forceinline__ F3 texture_value(const DeviceScene& S, uint32_t tex_idx, F3 p, float u = 0.0f, float v = 0.0f) {
   for (int depth = 0; depth < 8; depth++) {
     const float4 t0 = __ldg(S.textures + 3 * tex_idx), t1 = __ldg(S.textures + 3 * tex_idx + 1);
     const uint32_t type = __float_as_uint(t0.x);
@@ -57,6 +78,7 @@ __device__ __forceinline__ F3 texture_value(const DeviceScene& S, uint32_t tex_i
       tex_idx = ((ix + iy + iz) % 2 == 0) ? __float_as_uint(t0.y) : __float_as_uint(t0.z);
       continue;
     }
+    if (type == RT2_TEX_IMAGE) return image_value(S, __float_as_uint(__ldg(S.textures + 3 * tex_idx + 2).y), u, v);
     if (type == RT2_TEX_NOISE) {
       const float4 t2 = __ldg(S.textures + 3 * tex_idx + 2);
       const rt2_perlin* P = S.perlin + __float_as_uint(t0.w);
@@ -76,9 +98,10 @@ __device__ __forceinline__ F3 texture_value(const DeviceScene& S, uint32_t tex_i
 // texture_value for textures whose chain holds no noise texture (solid colours, checkers of solid colours): the cheap
 // subset the fused finish+shade kernel evaluates inline.  The host marks every material that can reach a noise texture
 // as deferred (Renderer::UploadScene), so the noise branch is never needed here.
-__device__ __forceinline__ F3 texture_value_simple(const DeviceScene& S, uint32_t tex_idx, F3 p) {
+__device__ __forceinline__ F3 texture_value_simple(const DeviceScene& S, uint32_t tex_idx, F3 p, float u, float v) {
   for (int depth = 0; depth < 8; depth++) {
     const float4 t0 = __ldg(S.textures + 3 * tex_idx), t1 = __ldg(S.textures + 3 * tex_idx + 1);
+    if (__float_as_uint(t0.x) == RT2_TEX_IMAGE) return image_value(S, __float_as_uint(__ldg(S.textures + 3 * tex_idx + 2).y), u, v);
     if (__float_as_uint(t0.x) != RT2_TEX_CHECKER) return {t1.x, t1.y, t1.z};
     int ix = static_cast<int>(floorf(t1.w * p.x)), iy = static_cast<int>(floorf(t1.w * p.y)), iz = static_cast<int>(floorf(t1.w * p.z));
     tex_idx = ((ix + iy + iz) % 2 == 0) ? __float_as_uint(t0.y) : __float_as_uint(t0.z);
@@ -113,14 +136,14 @@ __device__ __forceinline__ F3 refract3(F3 uv, F3 n, float eta) {
 // point, time unchanged).  r = the bounce's scatter draw (x,y: unit vector, z: dielectric xi).
 template <int kType>
 __device__ __forceinline__ F3 scatter(const DeviceScene& S, const float4 m0, const float4 m1, F3 d_in, F3 p, F3 n, bool front_face,
-                                      const uint4 r, F3& dir) {
+                                      const uint4 r, F3& dir, float tu = 0.0f, float tv = 0.0f) {
   if (kType == RT2_MAT_LAMBERTIAN || kType == RT2_MAT_TEXTURE) {
     // Material.cpp:47-69
     F3 u = unit_vector(u01(r.x), u01(r.y));
     dir = {n.x + u.x, n.y + u.y, n.z + u.z};
     if (near_zero(dir)) dir = n;
     if (kType == RT2_MAT_LAMBERTIAN) return {m1.x, m1.y, m1.z};
-    return texture_value(S, __float_as_uint(m0.y), p);
+    return texture_value(S, __float_as_uint(m0.y), p, tu, tv);
   }
   if (kType == RT2_MAT_METAL) {
     // Material.cpp:10-17: always scatters (no dot(scattered, normal) > 0 test)
@@ -149,7 +172,7 @@ __device__ __forceinline__ F3 scatter(const DeviceScene& S, const float4 m0, con
   }
   // RT2_MAT_ISOTROPIC, Material.cpp:76-83
   dir = unit_vector(u01(r.x), u01(r.y));
-  return texture_value(S, __float_as_uint(m0.y), p);
+  return texture_value(S, __float_as_uint(m0.y), p, tu, tv);
 }
 
 }  // namespace rt2dev

@@ -23,6 +23,9 @@ struct DeviceScene {
   const float4* __restrict__ materials;  // 2 x float4 per material
   const float4* __restrict__ textures;   // 3 x float4 per texture
   const rt2_perlin* __restrict__ perlin;
+  const uint4* __restrict__ images;        // {texel_offset, width, height, 0} per image texture
+  const float4* __restrict__ image_texels;  // linear RGBA, row 0 = top
+  uint32_t n_images;
   const uint32_t* __restrict__ prim_refs;
   const float4* __restrict__ nodes;  // 4 x float4 per node pair
   uint32_t tlas_root;
@@ -526,6 +529,7 @@ __device__ __forceinline__ bool medium_draw(float hit_dist, float ray_len, float
 struct HitOut {
   F3 p;
   float t;
+  float u, v;  // HitRecord::uv (only computed when the scene has image textures)
   F3 n;
   int32_t material;  // -1 = miss
   bool front_face;
@@ -582,6 +586,7 @@ __device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, f
   out.t = best.t;
   out.prim = best.prim;
   out.instance = best.instance;
+  out.u = out.v = 0.0f;
   if (medium_hit >= 0) {
     const uint4 m0 = __ldg(S.media + 2 * medium_hit), m1 = __ldg(S.media + 2 * medium_hit + 1);
     RaySpace rs = to_chain_space<M>(S, m1.x, m1.y, RaySpace{wo, wd});
@@ -626,6 +631,22 @@ __device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, f
     const float4 nd = __ldg(S.quads + 5 * idx), qq = __ldg(S.quads + 5 * idx + 1);
     outward = make_f3(nd);
     mat = __float_as_uint(qq.w);
+  }
+  if (S.n_images) {
+    if (RT2_PRIM_TYPE(best.prim) == RT2_PRIM_SPHERE) {
+      // Sphere::GetUV(outward_normal) (Sphere.cpp:34,39-43)
+      const float theta = acosf(-outward.y);
+      const float phi = atan2f(-outward.z, outward.x) + 3.14159265358979323846f;
+      out.u = phi / (2.0f * 3.14159265358979323846f);
+      out.v = theta / 3.14159265358979323846f;
+    } else {
+      // Quad::IsInterior stores the planar coordinates (Quad.cpp:15): alpha = w . ((p - q) x v), beta = w . (u x (p - q))
+      const float4 qq = __ldg(S.quads + 5 * idx + 1), uu = __ldg(S.quads + 5 * idx + 2), vv = __ldg(S.quads + 5 * idx + 3),
+                   ww = __ldg(S.quads + 5 * idx + 4);
+      const F3 ph = vsub<M>(p, make_f3(qq));
+      out.u = vdot<M>(make_f3(ww), vcross<M>(ph, make_f3(vv)));
+      out.v = vdot<M>(make_f3(ww), vcross<M>(make_f3(uu), ph));
+    }
   }
   // HitRecord::SetFaceNormal (HitRecord.hpp:17-20)
   bool ff = vdot<M>(rs.d, outward) < 0.0f;

@@ -11,6 +11,8 @@
 // say so in a warning.
 #include "scene_host.hpp"
 
+#include "image_in.hpp"
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -576,6 +578,38 @@ int ParseDocument(const json::Value& obj, const std::string& data_dir, uint64_t 
         rt2_perlin p;
         InitPerlin(&p, jt.GetInt("point_count", 256), rng);
         sc->perlin.push_back(p);
+      } else if (type == "image") {
+        // Schema extension: {"type": "image", "path": "<file relative to the data directory>"}.  Bytes are taken
+        // as sRGB-ish and linearised with the 2.2 power law stb_image's float loader applies (the book the reference follows
+        // loads its textures that way); a missing / undecodable file becomes a 1x1 cyan image, the book's debugging aid.
+        t.type = RT2_TEX_IMAGE;
+        albedo = V3{1, 1, 1};
+        std::string rel = jt.GetString("path", "");
+        std::string full = (!rel.empty() && rel[0] == '/') ? rel : data_dir + "/" + rel;
+        int iw = 0, ih = 0;
+        std::vector<uint8_t> rgb;
+        std::string ierr;
+        rt2_image img{};
+        img.texel_offset = static_cast<uint32_t>(sc->image_texels.size() / 4);
+        if (rel.empty() || !DecodeImageFile(full, &iw, &ih, &rgb, &ierr)) {
+          b.Warn("image texture: " + (rel.empty() ? std::string("no path") : ierr) + " (using solid cyan)");
+          iw = ih = 1;
+          sc->image_texels.insert(sc->image_texels.end(), {0.f, 1.f, 1.f, 1.f});
+        } else {
+          float lut[256];
+          for (int k = 0; k < 256; k++) lut[k] = std::pow(static_cast<float>(k) / 255.0f, 2.2f);
+          sc->image_texels.reserve(sc->image_texels.size() + rgb.size() / 3 * 4);
+          for (size_t k = 0; k + 2 < rgb.size(); k += 3) {
+            sc->image_texels.push_back(lut[rgb[k]]);
+            sc->image_texels.push_back(lut[rgb[k + 1]]);
+            sc->image_texels.push_back(lut[rgb[k + 2]]);
+            sc->image_texels.push_back(1.0f);
+          }
+        }
+        img.width = static_cast<uint32_t>(iw);
+        img.height = static_cast<uint32_t>(ih);
+        t.image_idx = static_cast<uint32_t>(sc->images.size());
+        sc->images.push_back(img);
       } else {
         // reference: prints "Invalid texture type" and still appends a default-constructed variant (SolidColor)
         b.Warn("Invalid texture type: " + type + " (kept as a black solid colour)");
@@ -884,6 +918,10 @@ void HostScene::FillDesc(rt2_scene_desc* d) const {
   d->width = width;
   d->height = height;
   d->camera = camera_block;
+  d->n_images = static_cast<uint32_t>(images.size());
+  d->n_image_texels = static_cast<uint32_t>(image_texels.size() / 4);
+  d->images = images.data();
+  d->image_texels = image_texels.data();
 }
 
 int LoadSceneString(const std::string& text, const std::string& data_dir, uint64_t perlin_seed, HostScene* out,

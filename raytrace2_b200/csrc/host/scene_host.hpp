@@ -38,6 +38,8 @@ struct HostScene {
   std::vector<rt2_material> materials;
   std::vector<rt2_texture> textures;
   std::vector<rt2_perlin> perlin;
+  std::vector<rt2_image> images;     // image textures (schema extension): table + one shared texel array
+  std::vector<float> image_texels;   // RGBA float32, linear light, row 0 = top
   std::vector<uint32_t> prim_refs;
   std::vector<rt2_bvh_node> nodes;  // 2 per pair
   uint32_t tlas_root{0};

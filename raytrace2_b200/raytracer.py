@@ -20,7 +20,7 @@ from . import _capi
 from ._capi import check, load_library
 
 HIT_DTYPE = np.dtype([("point", np.float32, 3), ("t", np.float32), ("normal", np.float32, 3), ("material", np.int32),
-                      ("prim", np.uint32), ("instance", np.int32), ("front_face", np.uint32), ("pad", np.uint32)])
+                      ("prim", np.uint32), ("instance", np.int32), ("front_face", np.uint32), ("uv16", np.uint32)])
 assert HIT_DTYPE.itemsize == C.sizeof(_capi.Hit)
 
 
@@ -113,6 +113,18 @@ class Scene:
     def textures(self):
         d = self.desc
         return _as_np(d.textures, d.n_textures, _capi.Texture)
+
+    def images(self):
+        """List of [H, W, 4] float32 arrays (linear RGBA, row 0 = top), one per image texture."""
+        d = self.desc
+        out = []
+        if d.n_images:
+            tab = _as_np(d.images, d.n_images, _capi.Image)
+            tex = np.ctypeslib.as_array(d.image_texels, shape=(d.n_image_texels, 4))
+            for im in tab:
+                o, w, h = int(im["texel_offset"]), int(im["width"]), int(im["height"])
+                out.append(tex[o:o + w * h].reshape(h, w, 4).copy())
+        return out
 
     def nodes(self):
         d = self.desc

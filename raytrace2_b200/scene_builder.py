@@ -51,6 +51,10 @@ class SceneBuilder:
         return self._push(self.textures, {"type": "noise", "scale": float(scale), "noise_type": 1 if marble else 0, "albedo": _v(albedo),
                                           "point_count": int(point_count)})
 
+    def image(self, path: str) -> int:
+        """Image texture (schema extension, include/rt2.h RT2_TEX_IMAGE): PNG / PPM file, path relative to the data directory."""
+        return self._push(self.textures, {"type": "image", "path": str(path)})
+
     # ---- materials (Serialize.cpp:244-285) ----
     def lambertian(self, albedo: Vec) -> int:
         return self._push(self.materials, {"type": "lambertian", "albedo": _v(albedo)})
