@@ -544,6 +544,7 @@ struct Renderer::Impl {
   uint32_t* sort_bin_base{nullptr};
   int grid_sort{0};
   int fs_blocks{4};  // resident blocks per SM the fused kernel is compiled for (4: 64 registers, a few spills; measured +1-2 %)
+  int trav_blocks{4};
   int trav_max_steps{8};  // node steps per round of the while-while traversal (measured: +12 % on the 1M-sphere scene, +1 % on book 2)
   int trav_fetch_threshold{kFetchThreshold};
   bool fused{true};               // k_finish_shade instead of k_finish_hit + per-bin shade kernels
@@ -625,7 +626,10 @@ int Renderer::Init(const HostScene& scene, const rt2_config& cfg) {
   if (cfg_.flags & RT2_FLAG_FAST_MATH) {
     RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<FastMath, false>, kBlock, 0));
   } else {
-    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false>, kBlock, 0));
+    if (const char* e = getenv("RT2_TRAV_BLOCKS")) m.trav_blocks = atoi(e);
+    if (m.trav_blocks == 5) RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false, 0, 5>, kBlock, 0));
+    else if (m.trav_blocks == 6) RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false, 0, 6>, kBlock, 0));
+    else RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false>, kBlock, 0));
   }
   if (occ < 1) occ = 1;
   m.grid_extend = sm_count_ * occ;
@@ -1166,6 +1170,8 @@ int Renderer::RenderBatch(uint32_t n_frames) {
       else k_traverse_flat<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, 0u, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav);
     } else if (exact) {
       if (profiling_) k_traverse<ExactMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
+      else if (m.trav_blocks == 5) k_traverse<ExactMath, false, 0, 5><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
+      else if (m.trav_blocks == 6) k_traverse<ExactMath, false, 0, 6><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
       else k_traverse<ExactMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
     } else {
       if (profiling_) k_traverse<FastMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
