@@ -775,16 +775,18 @@ int Renderer::UploadScene(const HostScene& scene) {
     UP(d_media, media, cap_media)
     UP(d_prim_refs, prim_refs, cap_prim_refs)
     {
-      // device node format: left_first of a LEAF holds the traversal entry (flag | (count-1) << 27 | first), so the
-      // node step of k_traverse uses it without decoding
+      // device node format: left_first holds the traversal entry (make_leaf_entry: a one-primitive leaf carries the
+      // primitive reference itself), count keeps the ABI values as count << 27 | left_first for rt2_read_bvh
       std::vector<rt2_bvh_node> dev_nodes = scene.nodes;
       for (rt2_bvh_node& nd : dev_nodes) {
         if (nd.count > 0) {
-          if (nd.count > 16 || nd.left_first >= (1u << 27)) {
-            err_ = "BVH leaf does not fit the 4-bit count / 27-bit index entry";
+          if (nd.count > 16 || nd.left_first >= (1u << 26) || nd.left_first + nd.count > scene.prim_refs.size()) {
+            err_ = "BVH leaf does not fit the 4-bit count / 26-bit index entry";
             return RT2_ERR_UNSUPPORTED;
           }
-          nd.left_first = kLeafFlag | ((nd.count - 1u) << 27) | nd.left_first;
+          const uint32_t first = nd.left_first, count = nd.count;
+          nd.left_first = make_leaf_entry(first, count, scene.prim_refs[first]);
+          nd.count = (count << 27) | first;
         }
       }
       rc = UploadBuf(m, &m.d_nodes, &m.cap_nodes, dev_nodes, &err_);
@@ -942,8 +944,8 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
     max_n = n > max_n ? n : max_n;
     if (k > 0) instances[k - 1].blas_root = pair_base[k];
   }
-  if (pairs >= 0x7FFFFFF0ull || refs >= 0x07FFFFFFull) {
-    err_ = "scene too large for the 27-bit primitive / 31-bit node index fields";
+  if (pairs >= 0x7FFFFFF0ull || refs >= 0x03FFFFFFull) {
+    err_ = "scene too large for the 26-bit primitive / 31-bit node index fields";
     return RT2_ERR_UNSUPPORTED;
   }
   int rc;
@@ -1003,8 +1005,13 @@ int Renderer::ReadBvh(rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs
       return RT2_ERR_INVALID_ARG;
     }
     RT2_CUDA(cudaMemcpy(nodes, m.d_nodes, 2ull * n_node_pairs_ * sizeof(rt2_bvh_node), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < 2ull * n_node_pairs_; i++)  // device format -> ABI format (see UploadScene)
-      if (nodes[i].count > 0) nodes[i].left_first &= 0x07FFFFFFu;
+    for (size_t i = 0; i < 2ull * n_node_pairs_; i++) {  // device format -> ABI format (see UploadScene)
+      if (nodes[i].count > 0) {
+        const uint32_t packed = nodes[i].count;
+        nodes[i].left_first = packed & 0x07FFFFFFu;
+        nodes[i].count = packed >> 27;
+      }
+    }
   }
   if (prim_refs) {
     if (max_refs < n_prim_refs_) {

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_refit(int n, const uint2* _
 __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_emit(int n, uint32_t pair_base, uint32_t ref_base, const uint2* __restrict__ children,
                                                           const float4* __restrict__ leaf_min, const float4* __restrict__ leaf_max,
                                                           const float4* __restrict__ node_min, const float4* __restrict__ node_max,
-                                                          float4* __restrict__ nodes_out) {
+                                                          const uint32_t* __restrict__ prim_refs, float4* __restrict__ nodes_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   const uint2 c = children[i];
@@ -320,8 +320,10 @@ __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_emit(int n, uint32_t pair_b
     if (link & kChildLeaf) {
       mn = leaf_min[idx];
       mx = leaf_max[idx];
-      left_first = kChildLeaf | (ref_base + idx);  // device node format: the traversal entry (leaf flag | (count-1) << 27 | first)
-      count = 1;
+      // device node format (rt_trace.cuh make_leaf_entry): a one-primitive leaf carries the primitive reference itself;
+      // .w of the max corner keeps the ABI values as count << 27 | left_first
+      left_first = kChildLeaf | 0x40000000u | prim_refs[ref_base + idx];
+      count = (1u << 27) | (ref_base + idx);
     } else {
       mn = node_min[idx];
       mx = node_max[idx];
@@ -342,8 +344,8 @@ __global__ void k_lbvh_tiny(int n, uint32_t pair_base, uint32_t ref_base, const 
   for (int k = 0; k < 4; k++) out[k] = make_float4(nanv, nanv, nanv, __uint_as_float(0u));
   if (n == 1) {
     const rt2::BuildPrim p = prims[0];
-    out[0] = make_float4(p.bmin[0], p.bmin[1], p.bmin[2], __uint_as_float(kChildLeaf | ref_base));
-    out[1] = make_float4(p.bmax[0], p.bmax[1], p.bmax[2], __uint_as_float(1u));
+    out[0] = make_float4(p.bmin[0], p.bmin[1], p.bmin[2], __uint_as_float(kChildLeaf | 0x40000000u | p.ref));
+    out[1] = make_float4(p.bmax[0], p.bmax[1], p.bmax[2], __uint_as_float((1u << 27) | ref_base));
     prim_refs_out[0] = p.ref;
   }
 }
@@ -443,7 +445,8 @@ int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, 
   k_lbvh_hierarchy<<<grid_n, kLbvhBlock, 0, stream>>>(kin, static_cast<int>(n), children, parent_internal, parent_leaf);
   k_lbvh_refit<<<grid_n, kLbvhBlock, 0, stream>>>(static_cast<int>(n), children, parent_internal, parent_leaf, leaf_min, leaf_max, node_min, node_max,
                                                   visit);
-  k_lbvh_emit<<<grid_n, kLbvhBlock, 0, stream>>>(static_cast<int>(n), pair_base, ref_base, children, leaf_min, leaf_max, node_min, node_max, nodes);
+  k_lbvh_emit<<<grid_n, kLbvhBlock, 0, stream>>>(static_cast<int>(n), pair_base, ref_base, children, leaf_min, leaf_max, node_min, node_max, d_prim_refs,
+                                                 nodes);
   *launches += 4;
   LBVH_CUDA(cudaGetLastError());
   return RT2_OK;

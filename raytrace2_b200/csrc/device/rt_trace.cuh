@@ -44,6 +44,14 @@ struct DeviceScene {
 constexpr float kFltMax = 3.402823466e+38f;  // kInfinity (Defs.hpp:17)
 constexpr uint32_t kStackSentinel = 0x7FFFFFFFu;
 constexpr uint32_t kLeafFlag = 0x80000000u;
+// Traversal entries (the .w of a node's min corner on the device):
+//   interior     child pair index                                              (bit 31 clear)
+//   direct leaf  kLeafFlag | kLeafDirect | primitive reference (type << 28 | index)  — the usual case: one primitive per leaf
+//   list leaf    kLeafFlag | (count - 1) << 26 | first                          — prim_refs[first .. first + count), count <= 16
+constexpr uint32_t kLeafDirect = 0x40000000u;
+__host__ __device__ inline uint32_t make_leaf_entry(uint32_t first, uint32_t count, uint32_t ref_if_single) {
+  return count == 1u ? (kLeafFlag | kLeafDirect | ref_if_single) : (kLeafFlag | ((count - 1u) << 26) | first);
+}
 constexpr int kStackSize = 64;
 #define RT2_STACK_GUARD if (sp < kStackSize)
 
@@ -298,7 +306,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         const float n1 = near1 * 0.999999f;
         const bool h1 = (n1 <= far1) && (n1 <= bound);
         // device node format (rt_kernels.cu UploadScene / rt_lbvh.cu): .w of the min corner is the traversal entry itself:
-        // interior -> child pair index; leaf -> flag | (count-1) << 27 | first
+        // (interior -> child pair index; leaf -> see make_leaf_entry)
         const uint32_t e0 = __float_as_uint(a0.w), e1 = __float_as_uint(b0.w);
         if (h0 && h1) {
           const bool swap = near1 < near0;
@@ -315,11 +323,12 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
       __syncwarp();
       // phase 2: leaves
       if (active && (cur & kLeafFlag)) {
-        const uint32_t first = cur & 0x07FFFFFFu;
-        const uint32_t count = ((cur >> 27) & 0xFu) + 1u;
+        const bool direct = (cur & kLeafDirect) != 0u;
+        const uint32_t first = cur & 0x03FFFFFFu;
+        const uint32_t count = direct ? 1u : (((cur >> 26) & 0xFu) + 1u);
         bool entered = false;
         for (uint32_t i = 0; i < count; i++) {
-          const uint32_t ref = __ldg(S.prim_refs + first + i);
+          const uint32_t ref = direct ? (cur & 0x3FFFFFFFu) : __ldg(S.prim_refs + first + i);
           const uint32_t type = RT2_PRIM_TYPE(ref), idx = RT2_PRIM_INDEX(ref);
           if (type == RT2_PRIM_SPHERE) {
             if (kCount) cnt.spheres++;

@@ -15,12 +15,14 @@ namespace rt2 {
 namespace {
 
 constexpr int kBins = 16;
-// Leaf policy: a range of <= MaxLeaf() primitives becomes a leaf when the SAH says splitting does not pay, with one
+// Leaf policy: a range of <= MaxLeaf() primitives becomes a leaf when the SAH says splitting does not pay (default 1: on
+// the GPU the leaf phase of the while-while walk runs at ~6 of 32 lanes, so one-primitive leaves measured 2-8 % faster
+// than leaves of up to 4, profiles/r01_notes.md; longer leaves only appear behind the depth guard), with one
 // node-pair visit costed as TravCost() primitive tests.  Overridable for tuning runs (RT2_BVH_MAX_LEAF, RT2_BVH_TRAV_COST).
 uint32_t MaxLeaf() {
   static const uint32_t v = [] {
     const char* e = std::getenv("RT2_BVH_MAX_LEAF");
-    int x = e ? std::atoi(e) : 4;
+    int x = e ? std::atoi(e) : 1;
     return static_cast<uint32_t>(x < 1 ? 1 : (x > 16 ? 16 : x));
   }();
   return v;
