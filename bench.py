@@ -34,9 +34,10 @@ DEFAULT_SCENE = "book2_final_scene_10000_samples"
 # algorithmic HBM bytes per ray of k_traverse: ray origin+time 16 + direction 16 read, closest-surface
 # record 16 written
 EXTEND_BYTES_PER_RAY = 16 + 16 + 16
-# DRAM bytes per ray of k_traverse from the committed `ncu --set full` capture (profiles/r01c_ncu_summary.txt): used for
-# roofline.traffic = per-ray traffic x rays per launch; None until a capture is recorded
-EXTEND_DRAM_BYTES_PER_RAY_NCU = 35.3
+# DRAM bytes per ray of k_traverse from the committed `ncu --set full` capture (profiles/r01d_ncu_summary.txt: 59.5 + 4.5 MB
+# for the ~1.9 M rays of bounce 2, 44.5 + 2.4 MB for the ~1.4 M rays of bounce 3): used for roofline.traffic = per-ray
+# traffic x rays per launch
+EXTEND_DRAM_BYTES_PER_RAY_NCU = 34.0
 # arithmetic credited per unit of algorithmic work: AABB slab test 30, sphere test 30 (to the
 # discriminant; a lower bound), quad test 57, instance visit 42
 FLOP_AABB, FLOP_SPHERE, FLOP_QUAD, FLOP_INSTANCE = 30, 30, 57, 42

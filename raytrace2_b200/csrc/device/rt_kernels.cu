@@ -1152,8 +1152,8 @@ int Renderer::RenderBatch(uint32_t n_frames) {
     uint32_t* next = m.counters + static_cast<size_t>(b + 1) * kCounterStride;
     const int out = in ^ 1;
     // coherence order of this bounce's queue (keys were written by the scatter kernels of the previous bounce)
-    const bool sorted = m.sort_enabled && b >= 1 && b <= m.sort_max_bounce;
-    const bool sort_next = m.sort_enabled && b + 1 <= m.sort_max_bounce;
+    const bool sorted = m.sort_enabled && !m.flat_mode && b >= 1 && b <= m.sort_max_bounce;  // the flat extend kernel has no use for an order
+    const bool sort_next = m.sort_enabled && !m.flat_mode && b + 1 <= m.sort_max_bounce;
     const uint32_t* order = nullptr;
     if (sorted) {
       prof(5);
