@@ -8,13 +8,15 @@ import numpy as np
 
 
 def z_scores(sum_a, sumsq_a, n_a, sum_b, sumsq_b, n_b):
-    """Per pixel and channel z = (m_A - m_B) / sqrt(s2_A/n_A + s2_B/n_B); zero-variance entries are masked out."""
+    """Per pixel and channel z = (m_A - m_B) / sqrt(s2_A/n_A + s2_B/n_B).  Entries without usable variance are masked out:
+    exactly zero, or below (1 % of the mean)^2 — for (nearly) deterministic pixels such as a constant background the
+    float32 sums of squares only hold accumulation noise, and the ratio of two rounding errors is not a z-score."""
     sum_a, sumsq_a, sum_b, sumsq_b = (np.asarray(x, np.float64) for x in (sum_a, sumsq_a, sum_b, sumsq_b))
     m_a, m_b = sum_a / n_a, sum_b / n_b
     v_a = np.maximum(sumsq_a / n_a - m_a * m_a, 0.0) * n_a / max(n_a - 1, 1)
     v_b = np.maximum(sumsq_b / n_b - m_b * m_b, 0.0) * n_b / max(n_b - 1, 1)
     se2 = v_a / n_a + v_b / n_b
-    valid = se2 > 0
+    valid = (se2 > 0) & ((v_a + v_b) > 1e-4 * np.maximum(np.abs(m_a), np.abs(m_b)) ** 2)
     z = np.zeros_like(m_a)
     z[valid] = (m_a[valid] - m_b[valid]) / np.sqrt(se2[valid])
     return z, valid
