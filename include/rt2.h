@@ -293,6 +293,17 @@ int rt2_read_accum(rt2_renderer* r, float* sum, float* sumsq);
 int rt2_write_accum(rt2_renderer* r, const float* sum, const float* sumsq, uint64_t frames);
 /* Device pointer of the W*H*4-float accumulator (rgb + pad) for an external reduce (NCCL / torch.distributed). */
 int rt2_accum_device_ptr(rt2_renderer* r, void** ptr, size_t* n_floats);
+/* Multi-GPU read-out over peer memory (one process per GPU on one NVLink / NVSwitch box).  Every rank exports
+ * an RT2_IPC_HANDLE_BYTES-byte handle of its accumulator (CUDA IPC handle + offset inside the exported allocation); the reading
+ * rank passes all ranks' handles (n_ranks x RT2_IPC_HANDLE_BYTES bytes, its own slot is ignored) and one kernel sums the peers' accumulators in rank order with P2P loads, divides by total_frames and writes
+ * the mean (W*H*3 floats) and / or the RGBA8 preview — reduce + NonConvertedPixels / Pixels in one pass.  The CALLER
+ * synchronises: every rank must have finished rendering (rt2_synchronize + a barrier) before the call, and must not
+ * touch its accumulator until the reading rank returns.  Handles stay valid until the exporting renderer is resized or
+ * destroyed. */
+#define RT2_IPC_HANDLE_BYTES 80
+int rt2_accum_ipc_handle(rt2_renderer* r, uint8_t* handle);
+int rt2_resolve_peers(rt2_renderer* r, const uint8_t* handles, uint32_t n_ranks, uint32_t self_rank, uint64_t total_frames,
+                      float* dst_mean_rgb, uint8_t* dst_rgba8);
 /* After an external reduce: declare how many frames the accumulator now holds in total. */
 int rt2_set_frame_idx(rt2_renderer* r, uint64_t frames);
 /* Fixed-ray parity hook ≡ scene.hittable_list.Hit(ray, Interval{tmin,tmax}) (RayTracer.cpp:25). rays: n x 8 floats

@@ -145,6 +145,8 @@ PROTOTYPES = {
     "rt2_write_accum": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "rt2_accum_device_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "rt2_set_frame_idx": (C.c_int, [_P, C.c_uint64]),
+    "rt2_accum_ipc_handle": (C.c_int, [_P, _P]),
+    "rt2_resolve_peers": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P]),
     "rt2_intersect": (C.c_int, [_P, _P, C.c_size_t, C.c_float, C.c_float, C.c_int, _P]),
     "rt2_read_bvh": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rt2_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),

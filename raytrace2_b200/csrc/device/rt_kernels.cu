@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rt_lbvh.hpp"
@@ -419,6 +420,39 @@ __global__ void __launch_bounds__(kBlock) k_resolve(uint32_t pixels, float frame
       const double cy = floor(static_cast<double>(fminf(fmaxf(my, 0.0f), 1.0f)) * 255.999);
       const double cz = floor(static_cast<double>(fminf(fmaxf(mz, 0.0f), 1.0f)) * 255.999);
       rgba8[p] = make_uchar4(static_cast<unsigned char>(cx), static_cast<unsigned char>(cy), static_cast<unsigned char>(cz), 255);
+    }
+  }
+}
+
+// Multi-GPU read-out fused into one kernel: rank 0 reads the accumulators of its peers straight out of their
+// HBM over NVLink (CUDA IPC mappings, P2P loads), adds them in rank order — so the N-GPU image has one defined summation
+// order —, divides by the total frame count and writes the mean and the RGBA8 preview.  Replaces reduce + resolve.
+constexpr int kMaxPeers = 16;
+struct PeerAccums {
+  const float4* p[kMaxPeers];
+};
+__global__ void __launch_bounds__(kBlock) k_resolve_peers(uint32_t pixels, float frames, PeerAccums peers, int n_ranks,
+                                                          float* __restrict__ mean_rgb, uchar4* __restrict__ rgba8) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += stride) {
+    float4 a = peers.p[0][i];
+    for (int r = 1; r < n_ranks; r++) {
+      const float4 v = peers.p[r][i];
+      a.x += v.x;
+      a.y += v.y;
+      a.z += v.z;
+    }
+    const float mx = a.x / frames, my = a.y / frames, mz = a.z / frames;
+    if (mean_rgb) {
+      mean_rgb[3 * i + 0] = mx;
+      mean_rgb[3 * i + 1] = my;
+      mean_rgb[3 * i + 2] = mz;
+    }
+    if (rgba8) {
+      const double cx = floor(static_cast<double>(fminf(fmaxf(mx, 0.0f), 1.0f)) * 255.999);
+      const double cy = floor(static_cast<double>(fminf(fmaxf(my, 0.0f), 1.0f)) * 255.999);
+      const double cz = floor(static_cast<double>(fminf(fmaxf(mz, 0.0f), 1.0f)) * 255.999);
+      rgba8[i] = make_uchar4(static_cast<unsigned char>(cx), static_cast<unsigned char>(cy), static_cast<unsigned char>(cz), 255);
     }
   }
 }
@@ -1067,7 +1101,13 @@ int Renderer::Resize(int w, int h) {
   m.bins.stride = static_cast<uint32_t>(N);
   RT2_CUDA(cudaMalloc(&m.counters, static_cast<size_t>(cfg_.max_depth + 1) * kCounterStride * sizeof(uint32_t)));
   RT2_CUDA(cudaMalloc(&m.radiance, N * sizeof(float4)));
-  RT2_CUDA(cudaMalloc(&m.accum, P * sizeof(float4)));
+  {
+    // a whole number of 2 MiB pages: the accumulator then owns its driver allocation, so that the CUDA IPC handle exported
+    // for the peer-memory read-out (rt2_accum_ipc_handle) names exactly this buffer (small cudaMalloc blocks are
+    // sub-allocated from shared 2 MiB pages, and an IPC handle always names the whole page)
+    const size_t page = 2ull << 20;
+    RT2_CUDA(cudaMalloc(&m.accum, (P * sizeof(float4) + page - 1) / page * page));
+  }
   if (cfg_.flags & RT2_FLAG_MOMENTS) RT2_CUDA(cudaMalloc(&m.accum_sq, P * sizeof(float4)));
   RT2_CUDA(cudaMalloc(&m.mean_rgb, P * 3 * sizeof(float)));
   RT2_CUDA(cudaMalloc(&m.rgba8, P * sizeof(uchar4)));
@@ -1394,6 +1434,86 @@ int Renderer::WriteAccum(const float* sum, const float* sumsq, uint64_t frames) 
   }
   frame_idx_ = frames;
   return RT2_OK;
+}
+
+// handle layout (RT2_IPC_HANDLE_BYTES = 80): cudaIpcMemHandle_t (64) | byte offset of the accumulator inside the exported
+// 2 MiB-aligned allocation (8) | reserved (8).  cudaIpcGetMemHandle names the whole driver allocation a pointer lives in
+// and cudaIpcOpenMemHandle returns that allocation's base in the peer (measured: with a sub-allocated 1 MiB accumulator
+// the peer read a neighbouring buffer).
+int Renderer::AccumIpcHandle(uint8_t* handle) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "layout of the exported handle");
+  cudaIpcMemHandle_t h;
+  RT2_CUDA(cudaIpcGetMemHandle(&h, m.accum));
+  // the accumulator is allocated in whole 2 MiB pages (Resize), so it starts its driver allocation; the offset field is kept
+  // for the page-relative position should that ever change
+  const unsigned long long offset = reinterpret_cast<unsigned long long>(m.accum) & ((2ull << 20) - 1ull);
+  std::memset(handle, 0, RT2_IPC_HANDLE_BYTES);
+  std::memcpy(handle, &h, 64);
+  std::memcpy(handle + 64, &offset, 8);
+  return RT2_OK;
+}
+
+int Renderer::ResolvePeers(const uint8_t* handles, uint32_t n_ranks, uint32_t self_rank, uint64_t total_frames, float* dst_mean,
+                           uint8_t* dst_rgba8) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (n_ranks < 1 || n_ranks > static_cast<uint32_t>(kMaxPeers) || self_rank >= n_ranks || (n_ranks > 1 && !handles)) {
+    err_ = "rt2_resolve_peers: bad rank arguments";
+    return RT2_ERR_INVALID_ARG;
+  }
+  const uint32_t P = static_cast<uint32_t>(width_) * height_;
+  const size_t b_mean = static_cast<size_t>(P) * 3 * sizeof(float), b_rgba = static_cast<size_t>(P) * 4;
+  // Every allocation this call needs is made BEFORE the peers are mapped, and the mappings are closed before returning:
+  // on the B200 boxes a cudaMallocHost issued while a lazily-enabled IPC mapping was open was handed the mapping's own
+  // virtual address (measured: the second read-out then read the staging buffer instead of the peer), so no mapping
+  // outlives the call.
+  int rc = EnsureStage(m, b_mean + b_rgba, &err_);
+  if (rc != RT2_OK) return rc;
+  const bool staged = m.h_stage_cap >= b_mean + b_rgba;
+  PeerAccums pa{};
+  void* opened[kMaxPeers];
+  int n_opened = 0;
+  auto close_all = [&]() {
+    for (int k = 0; k < n_opened; k++) cudaIpcCloseMemHandle(opened[k]);
+    n_opened = 0;
+  };
+  for (uint32_t r = 0; r < n_ranks; r++) {
+    if (r == self_rank) {
+      pa.p[r] = m.accum;
+      continue;
+    }
+    const uint8_t* hr = handles + static_cast<size_t>(RT2_IPC_HANDLE_BYTES) * r;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, hr, 64);
+    unsigned long long offset = 0;
+    std::memcpy(&offset, hr + 64, 8);
+    void* mapped = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      close_all();
+      err_ = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e);
+      return RT2_ERR_CUDA;
+    }
+    opened[n_opened++] = mapped;
+    pa.p[r] = reinterpret_cast<const float4*>(static_cast<const char*>(mapped) + offset);
+  }
+  k_resolve_peers<<<m.grid_stream, kBlock, 0, m.stream>>>(P, static_cast<float>(total_frames), pa, static_cast<int>(n_ranks),
+                                                          dst_mean ? m.mean_rgb : nullptr, dst_rgba8 ? m.rgba8 : nullptr);
+  launches_++;
+  cudaError_t e = cudaSuccess;
+  if (dst_mean) e = cudaMemcpyAsync(staged ? static_cast<void*>(m.h_stage) : dst_mean, m.mean_rgb, b_mean, cudaMemcpyDeviceToHost, m.stream);
+  if (e == cudaSuccess && dst_rgba8)
+    e = cudaMemcpyAsync(staged ? static_cast<void*>(m.h_stage + b_mean) : dst_rgba8, m.rgba8, b_rgba, cudaMemcpyDeviceToHost, m.stream);
+  rc = (e == cudaSuccess) ? Synchronize() : RT2_ERR_CUDA;
+  if (e != cudaSuccess) err_ = std::string("rt2_resolve_peers copy failed: ") + cudaGetErrorString(e);
+  close_all();
+  if (rc == RT2_OK && staged) {
+    if (dst_mean) std::memcpy(dst_mean, m.h_stage, b_mean);
+    if (dst_rgba8) std::memcpy(dst_rgba8, m.h_stage + b_mean, b_rgba);
+  }
+  return rc;
 }
 
 int Renderer::AccumDevicePtr(void** ptr, size_t* n_floats) {

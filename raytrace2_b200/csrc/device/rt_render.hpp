@@ -28,6 +28,8 @@ class Renderer {
   int ReadAccum(float* sum, float* sumsq);
   int WriteAccum(const float* sum, const float* sumsq, uint64_t frames);
   int AccumDevicePtr(void** ptr, size_t* n_floats);
+  int AccumIpcHandle(uint8_t* handle);
+  int ResolvePeers(const uint8_t* handles, uint32_t n_ranks, uint32_t self_rank, uint64_t total_frames, float* dst_mean, uint8_t* dst_rgba8);
   int Intersect(const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out);
   int GetStats(rt2_stats* out);
   int ReadBvh(rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs, size_t max_refs, uint32_t* n_pairs, uint32_t* n_refs,

@@ -206,6 +206,14 @@ int rt2_read_accum(rt2_renderer* r, float* sum, float* sumsq) { RT2_FORWARD(r->i
 int rt2_write_accum(rt2_renderer* r, const float* sum, const float* sumsq, uint64_t frames) {
   RT2_FORWARD(r->impl.WriteAccum(sum, sumsq, frames))
 }
+int rt2_accum_ipc_handle(rt2_renderer* r, uint8_t* handle) {
+  if (!handle) return Fail(RT2_ERR_INVALID_ARG, "null argument");
+  RT2_FORWARD(r->impl.AccumIpcHandle(handle))
+}
+int rt2_resolve_peers(rt2_renderer* r, const uint8_t* handles, uint32_t n_ranks, uint32_t self_rank, uint64_t total_frames, float* dst_mean_rgb,
+                      uint8_t* dst_rgba8) {
+  RT2_FORWARD(r->impl.ResolvePeers(handles, n_ranks, self_rank, total_frames, dst_mean_rgb, dst_rgba8))
+}
 int rt2_accum_device_ptr(rt2_renderer* r, void** ptr, size_t* n_floats) {
   if (!ptr || !n_floats) return Fail(RT2_ERR_INVALID_ARG, "null argument");
   RT2_FORWARD(r->impl.AccumDevicePtr(ptr, n_floats))

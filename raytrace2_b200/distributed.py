@@ -71,6 +71,21 @@ class DistributedRayTracer:
         dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM, group=self.group)
         return acc.numpy() if self.rank == 0 else None
 
+    def resolve_p2p(self, rgba8: bool = False) -> Optional[np.ndarray]:
+        """Read-out without a collective: rank 0 sums the peers' accumulators straight out of their HBM (CUDA IPC + NVLink
+        P2P loads) inside the resolve kernel (`rt2_resolve_peers`), in rank order — reduce + mean (+ RGBA8) in one pass.
+        One node, NCCL process group (the handles travel through `all_gather_object`)."""
+        dist = self.dist
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, self.tracer.accum_ipc_handle(), group=self.group)
+        self.tracer.synchronize()
+        dist.barrier(group=self.group)       # every rank has finished rendering
+        out = None
+        if self.rank == 0:
+            out = self.tracer.resolve_peers(handles, 0, self.total_frames, rgba8=rgba8)
+        dist.barrier(group=self.group)       # peers may touch their accumulators again
+        return out
+
     def NonConvertedPixels(self) -> Optional[np.ndarray]:
         """Mean over ALL ranks' frames on rank 0 (≡ RayTracer::NonConvertedPixels after `total_frames` Updates)."""
         total = self.reduce_accum()

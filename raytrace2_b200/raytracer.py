@@ -296,6 +296,26 @@ class RayTracer:
         check(self._lib.rt2_accum_device_ptr(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def accum_ipc_handle(self) -> bytes:
+        """RT2_IPC_HANDLE_BYTES (80) bytes naming the accumulator for peers (multi-GPU read-out over peer memory, rt2_resolve_peers)."""
+        buf = (C.c_uint8 * 80)()
+        check(self._lib.rt2_accum_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def resolve_peers(self, handles: Sequence[bytes], self_rank: int, total_frames: int, rgba8: bool = False) -> np.ndarray:
+        """Mean (or RGBA8 preview) over the accumulators of all ranks, summed in rank order by ONE kernel that reads the
+        peers' HBM over NVLink.  `handles[r]` = rank r's :meth:`accum_ipc_handle`.  The caller has synchronised all ranks."""
+        w, h = self.Dims()
+        blob = b"".join(bytes(x) for x in handles)
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        if rgba8:
+            out = np.empty((h, w, 4), np.uint8)
+            check(self._lib.rt2_resolve_peers(self._h, arr, len(handles), self_rank, total_frames, None, out.ctypes.data_as(C.c_void_p)))
+        else:
+            out = np.empty((h, w, 3), np.float32)
+            check(self._lib.rt2_resolve_peers(self._h, arr, len(handles), self_rank, total_frames, out.ctypes.data_as(C.c_void_p), None))
+        return out
+
     def set_frame_idx(self, frames: int) -> None:
         check(self._lib.rt2_set_frame_idx(self._h, frames))
 

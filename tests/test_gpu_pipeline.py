@@ -107,3 +107,31 @@ def test_checkpoint_resume_is_bit_identical(native_lib, tmp_path):
     other = rt.RayTracer(scene, **{**kw, "seed": 124})
     with pytest.raises(ValueError):
         other.load_checkpoint(ck)
+
+
+def test_resolve_peers_with_one_rank_equals_the_plain_read_out(native_lib):
+    """rt2_resolve_peers on a single rank (no peer mapping needed) is NonConvertedPixels / Pixels; the N-rank path runs under
+    torchrun in tools/dist_check.py (CUDA IPC cannot map an allocation into the process that owns it)."""
+    scene = rt.Scene.load(scene_path("cornell_original_test"))
+    tr = rt.RayTracer(scene, num_samples=16, seed=4, dims=(96, 96))
+    tr.Update(16)
+    handle = tr.accum_ipc_handle()
+    assert len(handle) == 80 and any(handle[:64])
+    a = tr.resolve_peers([handle], 0, 16)
+    assert np.array_equal(a.view(np.uint32), tr.NonConvertedPixels().view(np.uint32))
+    assert np.array_equal(tr.resolve_peers([handle], 0, 16, rgba8=True), tr.Pixels())
+    with pytest.raises(rt.Rt2Error):
+        tr.resolve_peers([handle], 3, 16)
+
+
+def test_two_gpu_read_out_paths(native_lib):
+    """tools/dist_check.py under torchrun with 2 ranks: peer-memory read-out == NCCL read-out == single-GPU render.  Needs two
+    visible GPUs (skipped on a one-GPU box; the driver's multi-GPU runs and profiles/r01_notes.md cover it there)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if native_lib.rt2_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29633", os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "dist_check OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
