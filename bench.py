@@ -124,7 +124,10 @@ class ClockSampler:
 def load_scene(rt, args):
     if args.scene.startswith("synthetic:"):
         n = int(args.scene.split(":")[1])
-        return rt.Scene.synthetic_spheres(n, width=args.width or 3840, height=args.height or 2160), f"synthetic {n}-sphere BVH stress scene"
+        # large instances skip the host SAH build (seconds per million spheres): the BVH is built on the device (run_ours adds
+        # RT2_FLAG_GPU_LBVH for them)
+        return (rt.Scene.synthetic_spheres(n, width=args.width or 3840, height=args.height or 2160, host_bvh=n < 2_000_000),
+                f"synthetic {n}-sphere BVH stress scene")
     path = os.path.join(ROOT, "data", args.scene + ".json")
     return rt.Scene.load(path, data_dir=os.path.join(ROOT, "data")), f"data/{args.scene}.json"
 
@@ -206,6 +209,8 @@ def run_ours(args):
     scene, scene_label = load_scene(rt, args)
     dims = (args.width, args.height) if args.width and args.height else None
     flags = rt.RT2_FLAG_FAST_MATH if args.fast_math else 0
+    if args.scene.startswith("synthetic:") and int(args.scene.split(":")[1]) >= 2_000_000:
+        flags |= rt.RT2_FLAG_GPU_LBVH
     tracer = rt.RayTracer(scene, num_samples=args.spp_total, max_depth=args.max_depth, device=local_rank, seed=20261018,
                           flags=flags, frames_per_batch=args.spp_per_step, frame_offset=rank, frame_stride=world, dims=dims)
     W, H = tracer.Dims()
