@@ -220,6 +220,9 @@ typedef struct rt2_renderer rt2_renderer;
                                      k_finish_shade (A/B and debugging; results are identical) */
 #define RT2_FLAG_GPU_LBVH 8u    /* build every BVH on the device (Morton codes + radix sort + Karras hierarchy) instead of
                                    uploading the host SAH trees */
+#define RT2_FLAG_WIDE_BVH 32u   /* with RT2_FLAG_GPU_LBVH, scenes without instances: collapse the device-built tree into 4-wide
+                                   nodes with 8-bit child boxes (64 B per node) and walk those — half the node traffic of the
+                                   binary tree; for scenes whose tree does not fit the caches (1 M - 10 M primitives) */
 #define RT2_FLAG_SORT_RAYS 16u  /* reorder every bounce's ray queue by (direction octant, origin cell) before the traversal
                                    (device radix sort); changes the traversal ORDER only, never a result */
 

@@ -24,6 +24,7 @@ RT2_FLAG_FAST_MATH = 2
 RT2_FLAG_NO_FUSED_SHADE = 4
 RT2_FLAG_GPU_LBVH = 8
 RT2_FLAG_SORT_RAYS = 16
+RT2_FLAG_WIDE_BVH = 32
 
 RT2_PRIM_SPHERE, RT2_PRIM_QUAD, RT2_PRIM_INSTANCE, RT2_PRIM_MEDIUM = 0, 1, 2, 3
 RT2_PRIM_NONE = 0xFFFFFFFF

@@ -27,6 +27,7 @@
 #include "rt_render.hpp"
 #include "rt_shade.cuh"
 #include "rt_sort.cuh"
+#include "rt_wide.cuh"
 
 namespace rt2dev {
 
@@ -141,6 +142,28 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_traverse(const DeviceSce
   traverse_queue<M, kCount, kFetchThreshold, kVar>(S, n, ray_o, ray_d, 0.001f, kFltMax, counters + 7, ord, trav, cnt, max_steps, fetch_threshold);
   if (kCount) {
     // warp-reduce, one atomic per warp and counter
+    uint32_t v[4] = {cnt.box_pairs, cnt.spheres, cnt.quads, cnt.instances};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t x = v[k];
+      for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
+      if ((threadIdx.x & 31u) == 0u && x) atomicAdd(&work_counters[k], static_cast<unsigned long long>(x));
+    }
+  }
+}
+
+// Extend, part 1 over the 4-wide quantised tree (rt_wide.cuh): scenes whose binary tree does not fit the caches.
+// counters == nullptr: fixed ray count and caller-supplied interval (rt2_intersect).
+template <class M, bool kCount>
+__global__ void __launch_bounds__(kBlock, 4) k_traverse_wide(const DeviceScene S, const WideScene W, uint32_t* __restrict__ counters,
+                                                            uint32_t n_fixed, uint32_t* __restrict__ cursor,
+                                                            const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float tmin,
+                                                            float tmax, uint4* __restrict__ trav,
+                                                            unsigned long long* __restrict__ work_counters, int max_steps) {
+  const uint32_t n = counters ? counters[0] : n_fixed;
+  TravCounters cnt;
+  traverse_queue_wide<M, kCount, kFetchThreshold>(S, W, n, ray_o, ray_d, tmin, tmax, counters ? counters + 7 : cursor, trav, cnt, max_steps);
+  if (kCount) {
     uint32_t v[4] = {cnt.box_pairs, cnt.spheres, cnt.quads, cnt.instances};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -538,6 +561,10 @@ struct Renderer::Impl {
   void* d_flat_bounds{nullptr};
   size_t cap_flat_refs{0}, cap_flat_offsets{0}, cap_flat_bounds{0};
   bool flat_mode{false};  // tiny scene: k_traverse_flat instead of the BVH walk
+  void* d_nodes4{nullptr};  // RT2_FLAG_WIDE_BVH: 4-wide quantised nodes collapsed from the device LBVH (rt_wide.cuh)
+  size_t cap_nodes4{0};
+  bool wide_mode{false};
+  WideScene wide{};
   // pinned host staging: scene uploads are packed into it (true async H2D), read-backs land in it (true async D2H)
   char* h_stage{nullptr};
   size_t h_stage_cap{0}, h_stage_used{0};
@@ -598,7 +625,7 @@ Renderer::~Renderer() {
   cudaSetDevice(cfg_.device);
   FreeState();
   Impl& m = *impl_;
-  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_flat_bounds, m.d_images, m.d_image_texels};
+  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_flat_bounds, m.d_images, m.d_image_texels, m.d_nodes4};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.totals) cudaFree(m.totals);
@@ -830,6 +857,11 @@ int Renderer::UploadScene(const HostScene& scene) {
     n_node_pairs_ = static_cast<uint32_t>(scene.nodes.size() / 2);
     n_prim_refs_ = static_cast<uint32_t>(scene.prim_refs.size());
     bvh_build_ms_ = 0;
+    m.wide_mode = false;
+    if (cfg_.flags & RT2_FLAG_WIDE_BVH) {
+      err_ = "RT2_FLAG_WIDE_BVH needs RT2_FLAG_GPU_LBVH (the wide tree is collapsed from the device-built tree)";
+      return RT2_ERR_INVALID_ARG;
+    }
   } else {
     rc = BuildTreesOnDevice(scene);
     if (rc != RT2_OK) return rc;
@@ -1014,6 +1046,21 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
                            static_cast<uint32_t*>(m.d_prim_refs), &m.lbvh_scratch, m.stream, &launches_, &err_);
     if (rc != RT2_OK) return rc;
     if (k + 1 < n_trees) RT2_CUDA(cudaStreamSynchronize(m.stream));  // d_build_prims is reused by the next tree
+  }
+  m.wide_mode = false;
+  if (cfg_.flags & RT2_FLAG_WIDE_BVH) {
+    if (!scene.instances.empty()) {
+      err_ = "RT2_FLAG_WIDE_BVH supports scenes without instances (the wide tree is a single world-space tree)";
+      return RT2_ERR_UNSUPPORTED;
+    }
+    const uint32_t n_pairs = static_cast<uint32_t>(pairs);
+    rc = ensure(&m.d_nodes4, &m.cap_nodes4, static_cast<size_t>(n_pairs) * 64);
+    if (rc != RT2_OK) return rc;
+    k_wide_collapse<<<(n_pairs + 255) / 256, 256, 0, m.stream>>>(static_cast<const float4*>(m.d_nodes), n_pairs, static_cast<uint4*>(m.d_nodes4));
+    launches_++;
+    m.wide.nodes4 = static_cast<const uint4*>(m.d_nodes4);
+    m.wide.root = pair_base[0];
+    m.wide_mode = scene.tree_prims[0].size() >= 2;  // a one-leaf tree has no node pair to collapse
   }
   RT2_CUDA(cudaEventRecord(m.ev_stop, m.stream));
   RT2_CUDA(cudaStreamSynchronize(m.stream));
@@ -1212,7 +1259,15 @@ int Renderer::RenderBatch(uint32_t n_frames) {
     prof(1);
     unsigned long long* work = m.totals + 2;
     const uint32_t smin = m.sort_min_rays;
-    if (m.flat_mode) {
+    if (m.wide_mode) {
+      if (exact) {
+        if (profiling_) k_traverse_wide<ExactMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, m.wide, ctr, 0u, nullptr, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav, work, m.trav_max_steps);
+        else k_traverse_wide<ExactMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, m.wide, ctr, 0u, nullptr, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav, work, m.trav_max_steps);
+      } else {
+        if (profiling_) k_traverse_wide<FastMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, m.wide, ctr, 0u, nullptr, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav, work, m.trav_max_steps);
+        else k_traverse_wide<FastMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, m.wide, ctr, 0u, nullptr, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav, work, m.trav_max_steps);
+      }
+    } else if (m.flat_mode) {
       if (exact) k_traverse_flat<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, 0u, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav);
       else k_traverse_flat<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, 0u, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav);
     } else if (exact) {
@@ -1565,7 +1620,15 @@ int Renderer::Intersect(const float* rays, size_t n, float tmin, float tmax, int
   const uint32_t grid = (n32 + kBlock - 1) / kBlock;
   const uint32_t tgrid = grid < static_cast<uint32_t>(m.grid_extend) ? grid : static_cast<uint32_t>(m.grid_extend);
   const uint32_t seed_lo = static_cast<uint32_t>(cfg_.seed), seed_hi = static_cast<uint32_t>(cfg_.seed >> 32);
-  if (m.flat_mode) {
+  if (m.wide_mode) {
+    if (cfg_.flags & RT2_FLAG_FAST_MATH) {
+      k_traverse_wide<FastMath, false><<<tgrid, kBlock, 0, m.stream>>>(m.ds, m.wide, nullptr, n32, d_cursor, d_o, d_d, tmin, tmax, d_trav, nullptr, m.trav_max_steps);
+      k_finish_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
+    } else {
+      k_traverse_wide<ExactMath, false><<<tgrid, kBlock, 0, m.stream>>>(m.ds, m.wide, nullptr, n32, d_cursor, d_o, d_d, tmin, tmax, d_trav, nullptr, m.trav_max_steps);
+      k_finish_intersect<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
+    }
+  } else if (m.flat_mode) {
     if (cfg_.flags & RT2_FLAG_FAST_MATH) {
       k_traverse_flat<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, nullptr, n32, d_o, d_d, tmin, tmax, d_trav);
       k_finish_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);

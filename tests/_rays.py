@@ -13,7 +13,10 @@ def scene_bounds(scene):
         if n["bmin"][0] <= n["bmax"][0]:  # skips empty slots (NaN bounds)
             lo = np.minimum(lo, np.array(n["bmin"]))
             hi = np.maximum(hi, np.array(n["bmax"]))
-    return np.maximum(lo, -1500.0), np.minimum(hi, 1500.0)
+    lo, hi = np.maximum(lo, -1500.0), np.minimum(hi, 1500.0)
+    bad = ~(np.isfinite(lo) & np.isfinite(hi) & (lo < hi))  # e.g. a scene without a host tree: sample a generic box
+    lo[bad], hi[bad] = -1500.0, 1500.0
+    return lo, hi
 
 
 def fixed_rays(scene, n: int, seed: int):

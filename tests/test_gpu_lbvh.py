@@ -162,3 +162,44 @@ def test_radix_sort_orders_morton_codes(native_lib):
     step = np.linalg.norm(np.diff(cc, axis=0), axis=1)
     rnd = np.linalg.norm(cc[np.random.default_rng(0).permutation(len(cc))][1:] - cc[:-1], axis=1)
     assert np.median(step) < 0.1 * np.median(rnd)
+
+
+# ---- 4-wide quantised tree (RT2_FLAG_WIDE_BVH, rt_wide.cuh) ------------------------------------------------------------
+def _wide_vs_binary(scene, n_rays, seed):
+    o, d, t = fixed_rays(scene, n_rays, seed=seed)
+    binary = rt.RayTracer(scene, flags=rt.RT2_FLAG_GPU_LBVH, dims=(64, 64))
+    wide = rt.RayTracer(scene, flags=rt.RT2_FLAG_GPU_LBVH | rt.RT2_FLAG_WIDE_BVH, dims=(64, 64))
+    b = binary.intersect(o, d, t, skip_media=True)
+    w = wide.intersect(o, d, t, skip_media=True)
+    assert np.array_equal(b["material"] >= 0, w["material"] >= 0)
+    hit = b["material"] >= 0
+    assert hit.sum() > n_rays // 20
+    # Same closest t, bit for bit — except where the reference arithmetic itself depends on WHICH spheres are tested: for a
+    # small sphere thousands of units from the ray origin the discriminant of Sphere::Hit cancels to an absolute error of ~1,
+    # so a sphere whose (looser, quantised) box the ray crosses can report a hit the other tree never evaluates.
+    same_t = b["t"][hit].view(np.uint32) == w["t"][hit].view(np.uint32)
+    assert same_t.mean() > 0.998, same_t.mean()
+    assert np.array_equal(b["point"][hit][same_t].view(np.uint32), w["point"][hit][same_t].view(np.uint32))
+    assert (b["prim"][hit][same_t] == w["prim"][hit][same_t]).mean() > 0.999                # exact ties aside
+    return binary, wide
+
+
+def test_wide_tree_gives_identical_hits_on_the_sphere_field(native_lib):
+    scene = rt.Scene.synthetic_spheres(200000, width=256, height=144, host_bvh=False)
+    binary, wide = _wide_vs_binary(scene, 80000, seed=12)
+    # the renders trace the same paths: same ray totals, same image
+    binary.Update(4)
+    wide.Update(4)
+    ra, rw = binary.stats()["rays"], wide.stats()["rays"]
+    assert abs(ra - rw) < 2e-3 * ra
+    same = np.all(binary.read_accum().view(np.uint32) == wide.read_accum().view(np.uint32), axis=-1)
+    assert same.mean() > 0.98
+
+
+def test_wide_tree_on_a_scene_file_and_its_limits(native_lib):
+    scene = rt.Scene.load(scene_path("final_render_book_1"))   # 484 spheres incl. the r = 1000 ground sphere, no instances
+    _wide_vs_binary(scene, 60000, seed=13)
+    with pytest.raises(rt.Rt2Error):                            # instances are not supported by the single wide tree
+        rt.RayTracer(rt.Scene.load(scene_path("cornell_original_test")), flags=rt.RT2_FLAG_GPU_LBVH | rt.RT2_FLAG_WIDE_BVH)
+    with pytest.raises(rt.Rt2Error):                            # needs the device-built tree
+        rt.RayTracer(scene, flags=rt.RT2_FLAG_WIDE_BVH)
