@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scene", default=DEFAULT_SCENE, help="scene name under data/ (or 'synthetic:<n_spheres>')")
-    ap.add_argument("--spp-per-step", type=int, default=64)
+    ap.add_argument("--spp-per-step", type=int, default=256, help="samples per pixel per step = one wavefront batch (92 M paths at 600x600)")
     ap.add_argument("--spp-total", type=int, default=10000, help="samples-per-pixel setting (fixes the stratification grid)")
     ap.add_argument("--max-depth", type=int, default=50)
     ap.add_argument("--width", type=int, default=0)
@@ -161,7 +161,7 @@ def run_reference(args):
         return 0
     threads = os.cpu_count() or 1
     dims = (args.width, args.height) if args.width and args.height else None
-    spp = max(1, args.spp_per_step // 8)  # bounded sample per step: the CPU is ~300x slower than one B200
+    spp = max(1, args.spp_per_step // 32)  # bounded sample per step: the CPU is ~600x slower than one B200
     if args.scene.startswith("synthetic:"):
         print(json.dumps({"impl": "reference", "unavailable": "the synthetic scene has no JSON file the reference could load"}))
         return 0
