@@ -128,9 +128,46 @@ __device__ __forceinline__ bool sphere_hit(const float4 s0, const float4 s1, F3 
 }
 
 // Quad::Hit (Quad.cpp:19-35): CLOSED interval [tmin, tmax], alpha/beta in closed [0,1].
-template <class M>
+// Axis-aligned quads (u.w carries 1 + the normal's axis, set by the host: every box face, every Cornell wall): normal and w
+// have one non-zero component (axis C), u and v one each, so in the reference's expressions every other product is an exact
+// zero and every sum with it returns the other operand unchanged.  Evaluating only the surviving terms — n_C d_C,
+// n_C o_C, component C of the two cross products, one multiply by w_C — gives the same bits with a third of the operations.
+template <class M, int C>
+__device__ __forceinline__ bool quad_hit_axis(const float4 nd, const float4* __restrict__ q, F3 o, F3 d, float tmin, float tmax,
+                                              float& t_out) {
+  constexpr int C1 = (C + 1) % 3, C2 = (C + 2) % 3;
+  auto comp = [](const F3& a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); };
+  auto comp4 = [](const float4& a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); };
+  const float nc = comp4(nd, C);
+  const float ndd = M::mul(nc, comp(d, C));
+  if (fabsf(ndd) <= 9.99999993922529e-09f) return false;
+  const float t = M::div(M::sub(nd.w, M::mul(nc, comp(o, C))), ndd);
+  if (!(tmin <= t && t <= tmax)) return false;
+  const float4 qq = __ldg(q + 1), uu = __ldg(q + 2), vv = __ldg(q + 3), ww = __ldg(q + 4);
+  // planar hit point minus q, only the two in-plane components are needed
+  const float ph1 = M::sub(M::add(comp(o, C1), M::mul(comp(d, C1), t)), comp4(qq, C1));
+  const float ph2 = M::sub(M::add(comp(o, C2), M::mul(comp(d, C2), t)), comp4(qq, C2));
+  // (ph x v)_C = ph_C1 v_C2 - v_C1 ph_C2 ;  (u x ph)_C = u_C1 ph_C2 - ph_C1 u_C2   (glm::cross, component C)
+  const float wc = comp4(ww, C);
+  const float alpha = M::mul(wc, M::sub(M::mul(ph1, comp4(vv, C2)), M::mul(comp4(vv, C1), ph2)));
+  const float beta = M::mul(wc, M::sub(M::mul(comp4(uu, C1), ph2), M::mul(ph1, comp4(uu, C2))));
+  if (!(0.0f <= alpha && alpha <= 1.0f) || !(0.0f <= beta && beta <= 1.0f)) return false;
+  t_out = t;
+  return true;
+}
+
+// kAxis: take the axis-aligned path where the quad allows it.  Only the flat extend kernel does (uniform loops, registers
+// to spare: Cornell +9 %); in the BVH walk and in the fused finish+shade kernel the three extra inlined variants cost more
+// in registers / spills than they save (book 2 -3.6 % when enabled everywhere).
+template <class M, bool kAxis = false>
 __device__ __forceinline__ bool quad_hit(const float4* __restrict__ q, F3 o, F3 d, float tmin, float tmax, float& t_out) {
   const float4 nd = __ldg(q + 0);
+  if (kAxis) {
+    const uint32_t axis_code = __float_as_uint(__ldg(q + 2).w);  // rt2_quad.pad0
+    if (axis_code == 1u) return quad_hit_axis<M, 0>(nd, q, o, d, tmin, tmax, t_out);
+    if (axis_code == 2u) return quad_hit_axis<M, 1>(nd, q, o, d, tmin, tmax, t_out);
+    if (axis_code == 3u) return quad_hit_axis<M, 2>(nd, q, o, d, tmin, tmax, t_out);
+  }
   F3 normal = make_f3(nd);
   float ndd = vdot<M>(normal, d);
   // std::fabs(n_dot_raydir) < 1e-8 with a double literal  <=>  |x| <= float(1e-8)
@@ -390,7 +427,7 @@ __device__ __forceinline__ void flat_test_range(const DeviceScene& S, uint32_t f
     if (RT2_PRIM_TYPE(ref) == RT2_PRIM_SPHERE) {
       h = sphere_hit<M>(__ldg(S.spheres + 2 * idx), __ldg(S.spheres + 2 * idx + 1), o, d, a, time, tmin, best.t, t);
     } else {
-      h = quad_hit<M>(S.quads + 5 * idx, o, d, tmin, best.t, t);
+      h = quad_hit<M, true>(S.quads + 5 * idx, o, d, tmin, best.t, t);
     }
     if (h && lane_on) {
       best.t = t;

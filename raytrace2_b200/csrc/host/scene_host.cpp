@@ -105,6 +105,23 @@ struct Builder {
     }
     g.d = d;
     g.material = material;
+    // Axis code for the device's Quad::Hit (rt_trace.cuh quad_hit): 1 + c when normal and w have their only non-zero
+    // component on axis c and u, v one non-zero component each (every face of a MakeBox and every Cornell wall).  The
+    // reference's arithmetic then multiplies by exact zeros everywhere else, so the terms that survive can be evaluated
+    // alone with bit-identical results.
+    {
+      auto single = [](const V3& a, int* axis) {
+        int n = 0;
+        for (int i = 0; i < 3; i++)
+          if (a[i] != 0.0f) *axis = i, n++;
+        return n == 1;
+      };
+      int cn = -1, cw = -1, cu = -1, cv = -1;
+      uint32_t code = 0;
+      if (single(normal, &cn) && single(w, &cw) && cn == cw && single(u, &cu) && single(v, &cv) && cu != cn && cv != cn && cu != cv)
+        code = 1u + static_cast<uint32_t>(cn);
+      std::memcpy(&g.pad0, &code, sizeof(code));
+    }
     *box = RefAABB{RefAABB{q, q + u + v}, RefAABB{q + u, q + v}};
     sc->quads.push_back(g);
     return (RT2_PRIM_QUAD << 28) | static_cast<uint32_t>(sc->quads.size() - 1);
