@@ -188,6 +188,29 @@ __global__ void __launch_bounds__(kBlock) k_traverse_flat(const DeviceScene S, c
   }
 }
 
+// Constant media as a pass of their own (scenes whose media have multi-primitive boundaries, e.g. the box-bounded smoke of
+// the Cornell-volume scene: 2 media x 6 exact quad tests per ray): uniform work with its own register budget and the
+// axis-aligned quad path, instead of living inside the register-starved fused kernel.  A medium that scatters in front of
+// the closest surface overwrites the ray's traversal record with {t, medium reference}; k_finish_shade<.., kMedia = false>
+// turns either into the hit record.
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_media(const DeviceScene S, const FrameParams fp, uint32_t bounce,
+                                                  const uint32_t* __restrict__ counters, const float4* __restrict__ ray_o,
+                                                  const float4* __restrict__ ray_d, const float4* __restrict__ state,
+                                                  uint4* __restrict__ trav) {
+  const uint32_t n = counters[0];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float4 o = ray_o[i], d = ray_d[i];
+    const uint4 tr = trav[i];
+    const RngKey key = key_of_slot(fp, __float_as_uint(state[i].w));
+    Closest best{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)};
+    int32_t mh = -1;
+    media_sample<M, true>(S, make_f3(o), make_f3(d), o.w, 0.001f, key, bounce, best, mh);
+    if (mh >= 0) trav[i] = make_uint4(__float_as_uint(best.t), (RT2_PRIM_MEDIUM << 28) | static_cast<uint32_t>(mh), 0xFFFFFFFFu, 0u);
+  }
+}
+
 // Extend, part 2: constant media against the closest surface, the winner's hit record, and the push of the ray index
 // into its material bin.  One thread per ray, uniform work.
 template <class M>
@@ -220,7 +243,7 @@ __global__ void __launch_bounds__(kBlock) k_finish_hit(const DeviceScene S, cons
 // hit0 / hit1 and their index pushed into the material bin; k_shade_scatter / k_shade_terminal then run on those bins
 // only, so one marble ray does not stall its 31 warp-mates.
 //   counters[0] = queue size; counters[1..6] = deferred bins; next_counters[0] = rays emitted inline so far.
-template <class M, int kMinBlocks = 4>
+template <class M, int kMinBlocks = 4, bool kMedia = true>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const DeviceScene S, const FrameParams fp, uint32_t bounce, int emit_next,
                                                          uint32_t* __restrict__ counters, uint32_t* __restrict__ next_counters,
                                                          const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
@@ -249,8 +272,19 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
       const uint32_t slot = __float_as_uint(st.w);
       const RngKey key = key_of_slot(fp, slot);
       HitOut h;
-      finish_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, bounce,
-                    false, h);
+      if (kMedia) {
+        finish_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, bounce,
+                      false, h);
+      } else {
+        // no media in the scene, or k_media ran before: a medium that won left its reference in the traversal record
+        Closest best{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)};
+        int32_t mh = -1;
+        if (tr.y != RT2_PRIM_NONE && RT2_PRIM_TYPE(tr.y) == RT2_PRIM_MEDIUM) {
+          mh = static_cast<int32_t>(RT2_PRIM_INDEX(tr.y));
+          best.prim = RT2_PRIM_NONE;
+        }
+        finish_record<M>(S, make_f3(o), make_f3(d), o.w, best, mh, h);
+      }
       if (h.material < 0) {
         // miss: T * background (RayTracer.cpp:25-27)
         radiance[slot] = make_float4(st.x * S.background[0], st.y * S.background[1], st.z * S.background[2], 0.0f);
@@ -561,6 +595,7 @@ struct Renderer::Impl {
   void* d_flat_bounds{nullptr};
   size_t cap_flat_refs{0}, cap_flat_offsets{0}, cap_flat_bounds{0};
   bool flat_mode{false};  // tiny scene: k_traverse_flat instead of the BVH walk
+  bool split_media{false};  // media with multi-primitive boundaries: k_media pass + media-free fused kernel
   void* d_nodes4{nullptr};  // RT2_FLAG_WIDE_BVH: 4-wide quantised nodes collapsed from the device LBVH (rt_wide.cuh)
   size_t cap_nodes4{0};
   bool wide_mode{false};
@@ -924,6 +959,9 @@ int Renderer::UploadScene(const HostScene& scene) {
       default: break;
     }
   }
+  m.split_media = false;
+  for (const rt2_medium& md : scene.media) m.split_media = m.split_media || md.boundary_count > 1;
+  if (const char* e = getenv("RT2_SPLIT_MEDIA")) m.split_media = !scene.media.empty() && atoi(e) != 0;
   // flat mode: list every leaf primitive by space when the scene is tiny
   m.flat_mode = false;
   d.flat_refs = nullptr;
@@ -1291,6 +1329,14 @@ int Renderer::RenderBatch(uint32_t n_frames) {
         k_finish_shade<ExactMath, 3><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
                                                                              m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
                                                                              m.ray_d[out], m.state[out], keys, m.radiance);
+      } else if (exact && (m.ds.n_media == 0 || m.split_media)) {
+        if (m.split_media) {
+          k_media<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav);
+          launches_++;
+        }
+        k_finish_shade<ExactMath, 4, false><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
+                                                                                   m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
+                                                                                   m.ray_d[out], m.state[out], keys, m.radiance);
       } else if (exact) {
         k_finish_shade<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
                                                                           m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],

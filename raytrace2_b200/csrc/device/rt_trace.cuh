@@ -465,7 +465,7 @@ __device__ __forceinline__ Closest traverse_flat(const DeviceScene& S, F3 wo, F3
 // reference BVH has Hit() called twice (quirk Q2): both calls see identical boundary records, so they are computed once.
 // Roots of one boundary primitive along the ray, independent of any interval: Sphere::Hit's two roots (Sphere.cpp:13-24)
 // or Quad::Hit's plane parameter when the point lies inside the quad (Quad.cpp:19-35); NaN = no root.
-template <class M>
+template <class M, bool kAxis = false>
 __device__ __forceinline__ void boundary_roots(const DeviceScene& S, uint32_t ref, F3 o, F3 d, float a, float time, float& r_lo,
                                                float& r_hi, bool& is_sphere) {
   const float nanv = __int_as_float(0x7FC00000);
@@ -486,7 +486,7 @@ __device__ __forceinline__ void boundary_roots(const DeviceScene& S, uint32_t re
     r_hi = M::div(M::add(h, sqrtd), a);
   } else {
     float t;
-    if (quad_hit<M>(S.quads + 5 * idx, o, d, -kFltMax, kFltMax, t)) r_lo = t;
+    if (quad_hit<M, kAxis>(S.quads + 5 * idx, o, d, -kFltMax, kFltMax, t)) r_lo = t;
   }
 }
 // What <primitive>::Hit(r, Interval(lo, kInfinity)) reports for the roots above: spheres use the open interval and prefer
@@ -507,13 +507,13 @@ __device__ __forceinline__ float boundary_candidate(float r_lo, float r_hi, bool
 // tmax), and a primitive's roots do not depend on the interval, so for short boundaries (a sphere, a box of 6 quads) the
 // roots are computed ONCE and both queries are answered from them — same values bit for bit, half the arithmetic.
 constexpr uint32_t kBoundaryRootsMax = 6;
-template <class M>
+template <class M, bool kAxis = false>
 __device__ __forceinline__ bool medium_boundary(const DeviceScene& S, const uint4 m0, F3 o, F3 d, float a, float time, float& t1,
                                                 float& t2) {
   if (m0.w == 1u) {  // a single primitive (the usual sphere-bounded medium)
     float lo, hi;
     bool sph;
-    boundary_roots<M>(S, __ldg(S.prim_refs + m0.z), o, d, a, time, lo, hi, sph);
+    boundary_roots<M, kAxis>(S, __ldg(S.prim_refs + m0.z), o, d, a, time, lo, hi, sph);
     t1 = boundary_candidate(lo, hi, sph, -kFltMax);
     if (!(t1 <= kFltMax)) return false;
     const float t1_eps = static_cast<float>(static_cast<double>(t1) + 0.0001);
@@ -530,7 +530,7 @@ __device__ __forceinline__ bool medium_boundary(const DeviceScene& S, const uint
       lo[k] = hi[k] = __int_as_float(0x7FC00000);
       sph[k] = false;
       if (k < m0.w) {
-        boundary_roots<M>(S, __ldg(S.prim_refs + m0.z + k), o, d, a, time, lo[k], hi[k], sph[k]);
+        boundary_roots<M, kAxis>(S, __ldg(S.prim_refs + m0.z + k), o, d, a, time, lo[k], hi[k], sph[k]);
         const float c = boundary_candidate(lo[k], hi[k], sph[k], -kFltMax);
         if (c <= q1) {  // NaN compares false
           q1 = c;
@@ -583,17 +583,15 @@ struct HitOut {
   int32_t instance;
 };
 
-// Second half of the closest-hit query ≡ scene.hittable_list.Hit(r, Interval{tmin, tmax}, rec) (RayTracer.cpp:25):
-// given the closest SURFACE (traverse_queue), sample the constant media against it and build the winner's record.
-template <class M>
-__device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, Closest best,
-                                           const RngKey& key, uint32_t bounce, bool skip_media, HitOut& out) {
-
-  // constant media (few per scene): each draws its free path against the current best raw t
-  int32_t medium_hit = -1;
+// Constant media (few per scene) against the closest surface so far: each draws its free path (ConstantMedium.cpp:14-58)
+// against the current best raw t and shrinks it when it scatters first.  medium_hit = index of the winner or -1.
+template <class M, bool kAxis = false>
+__device__ __forceinline__ void media_sample(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, const RngKey& key,
+                                             uint32_t bounce, Closest& best, int32_t& medium_hit) {
+  medium_hit = -1;
   uint4 draw = make_uint4(0, 0, 0, 0);
   bool have_draw = false;
-  if (!skip_media) {
+  {
     for (uint32_t m = 0; m < S.n_media; m++) {
       const uint4 m0 = __ldg(S.media + 2 * m), m1 = __ldg(S.media + 2 * m + 1);
       RaySpace rs = to_chain_space<M>(S, m1.x, m1.y, RaySpace{wo, wd});
@@ -614,7 +612,7 @@ __device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, f
       const float span = (best.t - fmaxf(tmin, 0.0f)) * ray_len * 1.00001f;
       if (hd1 > span && hd2 > span) continue;
       float t1, t2;
-      if (!medium_boundary<M>(S, m0, rs.o, rs.d, a, time, t1, t2)) continue;
+      if (!medium_boundary<M, kAxis>(S, m0, rs.o, rs.d, a, time, t1, t2)) continue;
       float t;
       if (medium_draw<M>(hd1, ray_len, t1, t2, tmin, best.t, t)) {
         best.t = t;
@@ -628,7 +626,11 @@ __device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, f
       }
     }
   }
+}
 
+// The winner's hit record: a medium scatter (medium_hit >= 0, at best.t), the closest surface best.prim, or a miss.
+template <class M>
+__device__ __forceinline__ void finish_record(const DeviceScene& S, F3 wo, F3 wd, float time, Closest best, int32_t medium_hit, HitOut& out) {
   out.t = best.t;
   out.prim = best.prim;
   out.instance = best.instance;
@@ -702,6 +704,16 @@ __device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, f
   out.n = n;
   out.front_face = ff;
   out.material = static_cast<int32_t>(mat);
+}
+
+// Second half of the closest-hit query ≡ scene.hittable_list.Hit(r, Interval{tmin, tmax}, rec) (RayTracer.cpp:25): given the
+// closest SURFACE (traverse_queue), sample the constant media against it and build the winner's record.
+template <class M>
+__device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, Closest best,
+                                           const RngKey& key, uint32_t bounce, bool skip_media, HitOut& out) {
+  int32_t medium_hit = -1;
+  if (!skip_media) media_sample<M>(S, wo, wd, time, tmin, key, bounce, best, medium_hit);
+  finish_record<M>(S, wo, wd, time, best, medium_hit, out);
 }
 
 }  // namespace rt2dev
