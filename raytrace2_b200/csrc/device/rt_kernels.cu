@@ -2,14 +2,19 @@
 //
 // Replaces RayTracer::Update / RayColor (src/cpu_raytrace/RayTracer.cpp:20-70) with a batch-synchronous wavefront:
 //
-//   k_generate            Camera::GetRay for F frames x W*H pixels            (Camera.hpp:50-67)
+//   k_generate            Camera::GetRay for F frames x W*H pixels                       (Camera.hpp:50-67)
 //   per bounce b < max_depth:
-//     k_extend            closest hit (BVH + instances + media), hit record, push ray index into its material bin
-//     k_shade_terminal    miss -> T*background, diffuse light -> T*emit        (RayTracer.cpp:25-34,44)
-//     k_shade_scatter<m>  one launch per material bin present in the scene: new ray + throughput, written to the
-//                         next queue at a position derived from the bin counters (no atomics, queue sorted by bin)
-//   k_accumulate          accum[pixel] += radiance[f][pixel] in frame order    (RayTracer.cpp:64)
-//   k_resolve             mean, RGBA8 preview                                  (RayTracer.cpp:16-18,65-66,105-112)
+//     [k_sort_*]          optional: coherence order of the queue                          (RT2_FLAG_SORT_RAYS, rt_sort.cuh)
+//     k_traverse          closest SURFACE: persistent while-while walk of TLAS -> instance BLAS (rt_trace.cuh);
+//       | k_traverse_flat   tiny scenes: every primitive, uniform loops, no tree
+//       | k_traverse_wide   RT2_FLAG_WIDE_BVH: 4-wide quantised nodes             (rt_wide.cuh)
+//     [k_media]           scenes whose media have list boundaries: media sampling as its own pass
+//     k_finish_shade      media (else), hit record, Material::Scatter / Emit inline, next ray appended to the next
+//                         queue (one atomic per 256-ray tile, grouped by material class)  (RayTracer.cpp:25-44)
+//     [k_shade_scatter<TEXTURE|ISOTROPIC>, k_shade_terminal]  only the noise-textured (deferred) materials' bins
+//     (RT2_FLAG_NO_FUSED_SHADE: k_finish_hit -> hit records in HBM -> one k_shade_* launch per material bin)
+//   k_accumulate          accum[pixel] += radiance[f][pixel] in frame order                (RayTracer.cpp:64)
+//   k_resolve | k_resolve_peers   mean, RGBA8 preview; across GPUs over peer memory        (RayTracer.cpp:16-18,65-66,105-112)
 //
 // Queue sizes live in device memory (counters[bounce][8]); kernels are launched with a persistent grid and loop
 // grid-stride over the count they read there, so no host synchronisation happens inside a batch.
