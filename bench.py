@@ -349,7 +349,7 @@ def run_ours(args):
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.scene.startswith("synthetic:"):
         threads = os.cpu_count() or 1
-        spp_cpu = args.cpu_sample_spp or max(2, min(64, int(round(2.5 * threads / 8))))
+        spp_cpu = args.cpu_sample_spp or max(2, min(128, int(round(15 * threads / 8))))  # ~10 s of wall clock on all host threads
         mr, pps, kind, sec, crays, wh = reference_sample(args.scene, dims, spp_cpu, args.spp_total, args.max_depth, threads)
         line["cpu_baseline"] = {"value": mr, "unit": "Mrays/s", "cores": threads, "kind": kind, "paths_per_s": pps,
                                 "sample": f"{spp_cpu} spp of the same workload at {wh[0]}x{wh[1]} ({sec:.1f} s)"}
