@@ -107,3 +107,41 @@ def test_gpu_textured_render_matches_restatement(native_lib, port_oracle, tmp_pa
     assert 0.5 < st["std_z"] < 1.06 and st["frac_gt3"] < 0.005, st
     tz = parity.tile_z_scores(s, ss, spp, rs, rss, spp, tile=20)
     assert np.abs(tz).max() < 4.5
+
+
+def test_unsupported_png_variants_fall_back_to_cyan_with_a_warning(native_lib, tmp_path):
+    """16-bit and interlaced PNGs are outside the decoder's subset: the texture becomes the 1x1 cyan placeholder (the scene
+    still loads), like a missing file."""
+    from PIL import Image
+    pic = make_picture(16, 8)
+    Image.fromarray(pic[..., 0].astype(np.uint16) * 257).save(tmp_path / "deep.png")
+    Image.fromarray(pic, "RGB").save(tmp_path / "ok.png")
+    # flip the interlace byte of a valid file (IHDR data byte 12) and fix nothing else: the decoder must reject it on the flag
+    raw = bytearray((tmp_path / "ok.png").read_bytes())
+    raw[8 + 8 + 12] = 1
+    (tmp_path / "interlaced.png").write_bytes(bytes(raw))
+    (tmp_path / "garbage.png").write_bytes(b"not an image at all")
+    for name in ("deep.png", "interlaced.png", "garbage.png"):
+        img = _scene_with(name, tmp_path).images()[0]
+        assert img.shape == (1, 1, 4) and np.array_equal(img[0, 0, :3], [0, 1, 1]), name
+    ok = _scene_with("ok.png", tmp_path).images()[0]
+    assert ok.shape == (8, 16, 4)
+
+
+def test_image_texture_through_a_checker(native_lib, port_oracle, tmp_path):
+    """An image texture as one of a checker's children: the (u, v) of the hit travel through the recursion (Texture.cpp:7-11)."""
+    from PIL import Image
+    pic = make_picture(32, 16)
+    Image.fromarray(pic, "RGB").save(tmp_path / "pic.png")
+    b = sb.SceneBuilder(width=32)
+    tex = b.checker(2.0, b.image("pic.png"), b.solid((0.1, 0.2, 0.3)))
+    b.place(b.sphere((0, 0, 0), 1.0, b.textured(tex)))
+    (tmp_path / "scene.json").write_text(b.to_json())
+    port = port_oracle.PortScene(str(tmp_path / "scene.json"), 4)
+    pts = np.float32([[0.5, 0.5, 0.5], [2.5, 0.5, 0.5], [-0.5, 0.5, 0.5]])   # floor(p / 2) parity: even, odd, odd
+    uv = np.float32([[0.25, 0.75], [0.25, 0.75], [0.9, 0.1]])
+    got = port.texture_value_uv(2, pts, uv)
+    h, w = pic.shape[:2]
+    i, j = min(int(0.25 * w), w - 1), min(int((1 - 0.75) * h), h - 1)
+    assert np.allclose(got[0], _lin(pic)[j, i], rtol=1e-6)
+    assert np.allclose(got[1], [0.1, 0.2, 0.3]) and np.allclose(got[2], [0.1, 0.2, 0.3])
