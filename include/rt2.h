@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define RT2_ABI_VERSION 2
+#define RT2_ABI_VERSION 3
 
 enum {
   RT2_OK = 0,
@@ -135,6 +135,11 @@ typedef struct rt2_perlin {
   float vec[256][4]; /* xyz + pad */
 } rt2_perlin;
 
+/* Instance split: a scene with 1..RT2_MAX_HOISTED_INSTANCES instances is traversed in two passes — the world-space surfaces
+ * first (a TLAS without instance leaves), then one {ray, instance} entry per instance whose world box the ray's remaining
+ * segment touches, with the world-to-model transforms converged across the warp (device/rt_trace.cuh). */
+#define RT2_MAX_HOISTED_INSTANCES 4
+
 /* BVH node, 32 bytes; nodes are stored as sibling PAIRS (64-byte aligned): pair p = nodes[2p], nodes[2p+1].
  * count == 0: interior, left_first = index of the child pair.  count > 0: leaf over prim_refs[left_first .. +count).
  * An empty slot has NaN bounds (never entered by the slab test). */
@@ -181,6 +186,10 @@ typedef struct rt2_scene_desc {
   uint32_t n_image_texels;   /* float4 texels over all images */
   const rt2_image* images;
   const float* image_texels; /* 4 * n_image_texels floats */
+  /* instance split (RT2_MAX_HOISTED_INSTANCES): a second world tree over the surfaces only, and the world boxes of the instances */
+  uint32_t has_world_tlas;   /* 1 iff tlas_world_root is valid (the scene has 1..RT2_MAX_HOISTED_INSTANCES instances) */
+  uint32_t tlas_world_root;  /* node-pair index */
+  const float* inst_bounds;  /* 8 floats per instance: min xyz, 0, max xyz, 0 (conservative, world space) */
 } rt2_scene_desc;
 
 /* ---- scene: replaces serialize::SceneLoader::LoadScene (src/Serialize.hpp:21-22, Serialize.cpp:199-360) plus the
@@ -224,10 +233,13 @@ typedef struct rt2_renderer rt2_renderer;
                                    nodes with 8-bit child boxes (64 B per node) and walk those — half the node traffic of the
                                    binary tree; for scenes whose tree does not fit the caches (1 M - 10 M primitives) */
 #define RT2_FLAG_SORT_RAYS 16u  /* reorder every bounce's ray queue by (direction octant, origin cell) before the traversal
-                                   (device radix sort); changes the traversal ORDER only, never a result */
+                                   (device radix sort); changes the traversal ORDER only, never a result.  Measured as a net
+                                   loss: compiled only into `make EXPERIMENTS=1` builds, RT2_ERR_UNSUPPORTED otherwise */
+#define RT2_FLAG_NO_INSTANCE_SPLIT 64u /* walk instances inline (one kernel, instance leaves in the TLAS) even when the scene
+                                   qualifies for the two-pass instance split (RT2_MAX_HOISTED_INSTANCES); A/B and debugging */
 
 typedef struct rt2_config {
-  int32_t device;            /* CUDA device ordinal */
+  int32_t device;            /* CUDA device ordinal (the first one when n_gpus > 1) */
   int32_t width, height;     /* 0 = scene dims */
   int32_t samples_per_pixel; /* AppSettings::num_samples -> Camera::SetSamplesPerPixel (App.cpp:129): stratification grid */
   int32_t max_depth;         /* AppSettings::max_depth -> RayTracer::max_depth (App.cpp:128) */
@@ -236,6 +248,14 @@ typedef struct rt2_config {
   int32_t frame_stride;      /*   frame_offset + k * frame_stride, k = 0,1,...  (stride 0 or 1 = all frames) */
   uint32_t flags;
   uint64_t seed;             /* Philox key; the reference seeds from std::random_device (Math.hpp:11) */
+  int32_t n_gpus;            /* 0 or 1: one GPU (`device`).  N > 1: devices device .. device+N-1 of this box.  -1: every visible
+                                device.  The handle then owns one replica per GPU in THIS process: the frames
+                                of every rt2_update are dealt round-robin (global frame f goes to replica f mod N, which keeps
+                                each GPU's strata spread over the sqrt(spp) x sqrt(spp) grid, RayTracer.cpp:59-60), and every
+                                read-out sums the replicas' accumulators in replica order inside ONE kernel on the first GPU
+                                that reads the peers' HBM over NVLink (cudaDeviceEnablePeerAccess; staged copies when two
+                                devices have no peer path).  Images differ from the 1-GPU image by fp32 summation order only. */
+  int32_t reserved;
 } rt2_config;
 
 typedef struct rt2_stats {
@@ -255,6 +275,10 @@ typedef struct rt2_stats {
   uint64_t quad_tests;
   uint64_t instance_visits;
   double gpu_ms_sort; /* ... of the ray-sort kernels (RT2_FLAG_SORT_RAYS) */
+  uint64_t stack_overflows; /* warps whose traversal found the 64-entry stack full (0 in a valid render; read-outs fail otherwise) */
+  uint64_t pending_frames;  /* always 0 here: rt2_get_stats traces every requested frame first */
+  uint32_t n_gpus;          /* replicas behind this handle */
+  uint32_t instance_split;  /* 1 iff the two-pass instance split is active */
 } rt2_stats;
 
 typedef struct rt2_hit {
@@ -277,10 +301,16 @@ int rt2_upload_scene(rt2_renderer* r, const rt2_scene* scene);
 int rt2_resize(rt2_renderer* r, int32_t width, int32_t height);
 /* RayTracer::Reset (RayTracer.cpp:49-53): zero the accumulators and the frame index. */
 int rt2_reset(rt2_renderer* r);
-/* n_frames x RayTracer::Update (RayTracer.cpp:55-70): +1 sample per pixel each. Asynchronous on the renderer's stream. */
+/* n_frames x RayTracer::Update (RayTracer.cpp:55-70): +1 sample per pixel each.  The reference's app calls Update once per
+ * sample (App.cpp:244-246); here requested frames are collected until a wavefront batch (frames_per_batch per GPU) is full and
+ * traced then, asynchronously on the renderer's stream(s) — or by the next call that needs them (any rt2_read_*, rt2_flush,
+ * rt2_synchronize, rt2_get_stats, ...).  A frame's stratum and random numbers depend only on its index, so 10 000 calls with
+ * n_frames = 1 give the same image as one call with n_frames = 10 000, at the same speed. */
 int rt2_update(rt2_renderer* r, uint32_t n_frames);
+/* Trace every frame requested so far (asynchronous); rt2_synchronize also waits for the GPU(s). */
+int rt2_flush(rt2_renderer* r);
 int rt2_synchronize(rt2_renderer* r);
-/* RayTracer::FrameIdx (RayTracer.hpp:23) — local frames accumulated on this renderer. */
+/* RayTracer::FrameIdx (RayTracer.hpp:23) — frames requested from this renderer since the last reset (traced or pending). */
 int rt2_frame_idx(const rt2_renderer* r, uint64_t* out);
 /* RayTracer::Dims (RayTracer.hpp:29) */
 int rt2_dims(const rt2_renderer* r, int32_t* width, int32_t* height);
@@ -312,6 +342,10 @@ int rt2_set_frame_idx(rt2_renderer* r, uint64_t frames);
 /* Fixed-ray parity hook ≡ scene.hittable_list.Hit(ray, Interval{tmin,tmax}) (RayTracer.cpp:25). rays: n x 8 floats
  * (origin xyz, time, direction xyz, pad). Media are sampled with Philox keyed on the ray index unless skip_media != 0. */
 int rt2_intersect(rt2_renderer* r, const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out);
+/* Fixed-point parity hook for the device texture code ≡ textures[tex_idx]->Value(u, v, p) (Texture.hpp:14-17, Texture.cpp:7-22,
+ * PerlinNoiseGen.cpp:52-88), evaluated by the same device function the shade kernels call.  points: n x 3 floats, uv: n x 2
+ * floats or NULL (0, 0), rgb: n x 3 floats out. */
+int rt2_texture_value(rt2_renderer* r, uint32_t tex_idx, const float* points, const float* uv, size_t n, float* rgb);
 /* Copies the BVH the device traverses back to the host (inspection / tests): nodes = 2 * n_pairs entries. Pass NULL
  * buffers to query the sizes only. */
 int rt2_read_bvh(rt2_renderer* r, rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs, size_t max_refs, uint32_t* n_pairs,
@@ -327,7 +361,9 @@ int rt2_write_image(const float* mean_rgb, int32_t width, int32_t height, const 
 int rt2_tonemap_rgb8(const float* mean_rgb, int32_t width, int32_t height, uint8_t* dst);
 
 /* ---- app: the headless branch of App::Run (src/App.cpp:81-130,157,163-174,243-248) -------------------------------
- * argv as given to `raytrace_2 [scene[.json]] [out.png]`; settings_path ≡ <SRC_PATH>/local/data/settings.json. */
+ * argv as given to `raytrace_2 [scene[.json]] [out.png]`; settings_path ≡ <SRC_PATH>/local/data/settings.json.  Renders on
+ * every GPU of the box by default.  Extensions (removed from argv before the reference's positional parsing):
+ * `--gpus N` (1..visible), `--spp N` (overrides settings.num_samples), `--max-depth N`, `--seed N`. */
 int rt2_app_run(int argc, const char* const* argv, const char* settings_path, const char* data_dir);
 
 const char* rt2_last_error(void);
@@ -336,6 +372,9 @@ int rt2_device_count(void);
 /* Measured FP32 FMA peak of a device in TFLOP/s (micro-benchmark kernel; the roofline denominator of the instruction-bound
  * kernels). */
 int rt2_measure_fp32_peak(int32_t device, double* tflops);
+/* Measured L2 read bandwidth of a device in GB/s (a working set that stays L2-resident, read repeatedly with 16-byte loads):
+ * the roofline of traversals whose tree lives in L2 but not in L1. */
+int rt2_measure_l2_bandwidth(int32_t device, double* gbs);
 
 #ifdef __cplusplus
 }

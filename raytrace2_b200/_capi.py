@@ -25,6 +25,9 @@ RT2_FLAG_NO_FUSED_SHADE = 4
 RT2_FLAG_GPU_LBVH = 8
 RT2_FLAG_SORT_RAYS = 16
 RT2_FLAG_WIDE_BVH = 32
+RT2_FLAG_NO_INSTANCE_SPLIT = 64
+RT2_MAX_HOISTED_INSTANCES = 4
+RT2_ABI_VERSION = 3
 
 RT2_PRIM_SPHERE, RT2_PRIM_QUAD, RT2_PRIM_INSTANCE, RT2_PRIM_MEDIUM = 0, 1, 2, 3
 RT2_PRIM_NONE = 0xFFFFFFFF
@@ -98,20 +101,23 @@ class SceneDesc(C.Structure):
         ("background", C.c_float * 3), ("min_inv_scale", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
         ("camera", Camera),
         ("n_images", C.c_uint32), ("n_image_texels", C.c_uint32), ("images", C.POINTER(Image)), ("image_texels", C.POINTER(C.c_float)),
+        ("has_world_tlas", C.c_uint32), ("tlas_world_root", C.c_uint32), ("inst_bounds", C.POINTER(C.c_float)),
     ]
 
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("samples_per_pixel", C.c_int32),
                 ("max_depth", C.c_int32), ("frames_per_batch", C.c_int32), ("frame_offset", C.c_int32),
-                ("frame_stride", C.c_int32), ("flags", C.c_uint32), ("seed", C.c_uint64)]
+                ("frame_stride", C.c_int32), ("flags", C.c_uint32), ("seed", C.c_uint64), ("n_gpus", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("frames", C.c_uint64), ("launches", C.c_uint64),
                 ("gpu_ms_total", C.c_double), ("gpu_ms_extend", C.c_double), ("gpu_ms_shade", C.c_double),
                 ("gpu_ms_other", C.c_double), ("gpu_ms_finish", C.c_double), ("gpu_ms_bvh_build", C.c_double), ("box_pair_tests", C.c_uint64),
-                ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64), ("gpu_ms_sort", C.c_double)]
+                ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64), ("gpu_ms_sort", C.c_double),
+                ("stack_overflows", C.c_uint64), ("pending_frames", C.c_uint64), ("n_gpus", C.c_uint32), ("instance_split", C.c_uint32)]
 
 
 class Hit(C.Structure):
@@ -137,6 +143,7 @@ PROTOTYPES = {
     "rt2_resize": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "rt2_reset": (C.c_int, [_P]),
     "rt2_update": (C.c_int, [_P, C.c_uint32]),
+    "rt2_flush": (C.c_int, [_P]),
     "rt2_synchronize": (C.c_int, [_P]),
     "rt2_frame_idx": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rt2_dims": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
@@ -149,6 +156,7 @@ PROTOTYPES = {
     "rt2_accum_ipc_handle": (C.c_int, [_P, _P]),
     "rt2_resolve_peers": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P]),
     "rt2_intersect": (C.c_int, [_P, _P, C.c_size_t, C.c_float, C.c_float, C.c_int, _P]),
+    "rt2_texture_value": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_size_t, _P]),
     "rt2_read_bvh": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rt2_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "rt2_set_profiling": (C.c_int, [_P, C.c_int]),
@@ -160,6 +168,7 @@ PROTOTYPES = {
     "rt2_abi_version": (C.c_int, []),
     "rt2_device_count": (C.c_int, []),
     "rt2_measure_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
+    "rt2_measure_l2_bandwidth": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
 }
 
 _lib = None

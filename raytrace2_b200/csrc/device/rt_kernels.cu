@@ -31,14 +31,18 @@
 #include "rt_lbvh.hpp"
 #include "rt_render.hpp"
 #include "rt_shade.cuh"
-#include "rt_sort.cuh"
+#ifdef RT2_WITH_RAY_SORT
+#include "rt_sort.cuh"  // measured net loss (profiles/r01_notes.md): only in `make EXPERIMENTS=1` builds
+#endif
 #include "rt_wide.cuh"
+#include "../host/tuning.hpp"
 
 namespace rt2dev {
 
 constexpr int kBlock = 256;
 constexpr int kNumBins = 6;  // 0 terminal (miss / light), 1 lambertian, 2 texture, 3 metal, 4 dielectric, 5 isotropic
-constexpr int kCounterStride = 8;  // [0] queue size, [1..6] material bins, [7] traversal fetch cursor
+constexpr int kCounterStride = 12;  // [0] queue size, [1..6] material bins, [7] traversal fetch cursor,
+                                    // [8] instance-split entries of the bounce, [9] their fetch cursor
 constexpr int kFetchThreshold = 20;  // lanes: below this a warp refills its idle lanes from the queue
 
 struct FrameParams {
@@ -131,52 +135,52 @@ struct BinQueues {
   __host__ __device__ uint32_t* q(int bin) const { return base + static_cast<size_t>(bin) * stride; }
 };
 
-// Extend, part 1: closest SURFACE for every queued ray of this bounce (persistent warps, dynamic ray fetch).
-// counters[7] of the bounce is the queue's fetch cursor (zeroed with the other counters at batch start).
-template <class M, bool kCount, int kVar = 0, int kMinBlocks = 1>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) k_traverse(const DeviceScene S, uint32_t* __restrict__ counters,
-                                                     const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
-                                                     const uint32_t* __restrict__ order, uint32_t sort_min_rays,
-                                                     uint4* __restrict__ trav, unsigned long long* __restrict__ work_counters,
-                                                     int max_steps, int fetch_threshold) {
-  const uint32_t n = counters[0];
-  TravCounters cnt;
-  // queues below the threshold were not sorted (rt_sort.cuh): consume them in queue order
-  const uint32_t* ord = (order != nullptr && n >= sort_min_rays) ? order : nullptr;
-  // scene.hittable_list.Hit(scene, r, Interval{0.001, kInfinity}, rec)  (RayTracer.cpp:25)
-  traverse_queue<M, kCount, kFetchThreshold, kVar>(S, n, ray_o, ray_d, 0.001f, kFltMax, counters + 7, ord, trav, cnt, max_steps, fetch_threshold);
-  if (kCount) {
+// Extend, part 1: closest SURFACE for every queued ray of this bounce (persistent warps, dynamic fetch; rt_trace.cuh).
+//   kTravInline / kTravWorld: one item = one ray of the queue;  kTravInst: one item = one {ray, instance} entry.
+// n_ptr: device-resident item count (queue size, or the bounce's entry counter); nullptr: n_fixed (rt2_intersect).
+// cursor: the fetch cursor of the queue (zeroed with the other counters at batch start).
+__device__ __forceinline__ void flush_trav_counters(const TravCounters& cnt, bool count_work, unsigned long long* __restrict__ totals) {
+  if (count_work) {
     // warp-reduce, one atomic per warp and counter
     uint32_t v[4] = {cnt.box_pairs, cnt.spheres, cnt.quads, cnt.instances};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       uint32_t x = v[k];
       for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
-      if ((threadIdx.x & 31u) == 0u && x) atomicAdd(&work_counters[k], static_cast<unsigned long long>(x));
+      if ((threadIdx.x & 31u) == 0u && x) atomicAdd(&totals[2 + k], static_cast<unsigned long long>(x));
     }
   }
+  if (cnt.overflow) atomicAdd(&totals[6], 1ull);  // never expected: the builders bound the tree depth
+}
+
+template <class M, bool kCount, int kMode>
+__global__ void __launch_bounds__(kBlock, 4) k_traverse(const DeviceScene S, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
+                                                        uint32_t* __restrict__ cursor, const float4* __restrict__ ray_o,
+                                                        const float4* __restrict__ ray_d, float tmin, float tmax,
+                                                        const uint32_t* __restrict__ order, uint32_t sort_min_rays, uint4* trav,
+                                                        const SplitIO io, unsigned long long* __restrict__ totals, int max_steps,
+                                                        int fetch_threshold) {
+  const uint32_t n = n_ptr ? *n_ptr : n_fixed;
+  TravCounters cnt;
+  // queues below the threshold were not sorted (rt_sort.cuh): consume them in queue order
+  const uint32_t* ord = (order != nullptr && n >= sort_min_rays) ? order : nullptr;
+  // scene.hittable_list.Hit(scene, r, Interval{0.001, kInfinity}, rec)  (RayTracer.cpp:25)
+  traverse_queue<M, kCount, kMode>(S, n, ray_o, ray_d, tmin, tmax, cursor, ord, trav, io, cnt, max_steps, fetch_threshold);
+  flush_trav_counters(cnt, kCount, totals);
 }
 
 // Extend, part 1 over the 4-wide quantised tree (rt_wide.cuh): scenes whose binary tree does not fit the caches.
-// counters == nullptr: fixed ray count and caller-supplied interval (rt2_intersect).
+// n_ptr == nullptr: fixed ray count and caller-supplied interval (rt2_intersect).
 template <class M, bool kCount>
-__global__ void __launch_bounds__(kBlock, 4) k_traverse_wide(const DeviceScene S, const WideScene W, uint32_t* __restrict__ counters,
+__global__ void __launch_bounds__(kBlock, 4) k_traverse_wide(const DeviceScene S, const WideScene W, const uint32_t* __restrict__ n_ptr,
                                                             uint32_t n_fixed, uint32_t* __restrict__ cursor,
                                                             const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float tmin,
                                                             float tmax, uint4* __restrict__ trav,
-                                                            unsigned long long* __restrict__ work_counters, int max_steps) {
-  const uint32_t n = counters ? counters[0] : n_fixed;
+                                                            unsigned long long* __restrict__ totals, int max_steps) {
+  const uint32_t n = n_ptr ? *n_ptr : n_fixed;
   TravCounters cnt;
-  traverse_queue_wide<M, kCount, kFetchThreshold>(S, W, n, ray_o, ray_d, tmin, tmax, counters ? counters + 7 : cursor, trav, cnt, max_steps);
-  if (kCount) {
-    uint32_t v[4] = {cnt.box_pairs, cnt.spheres, cnt.quads, cnt.instances};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      uint32_t x = v[k];
-      for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
-      if ((threadIdx.x & 31u) == 0u && x) atomicAdd(&work_counters[k], static_cast<unsigned long long>(x));
-    }
-  }
+  traverse_queue_wide<M, kCount, kFetchThreshold>(S, W, n, ray_o, ray_d, tmin, tmax, cursor, trav, cnt, max_steps);
+  flush_trav_counters(cnt, kCount, totals);
 }
 
 // Extend, part 1 for tiny scenes (DeviceScene::flat_*): one thread per ray, uniform loops, no tree (traverse_flat).
@@ -202,12 +206,12 @@ template <class M>
 __global__ void __launch_bounds__(kBlock) k_media(const DeviceScene S, const FrameParams fp, uint32_t bounce,
                                                   const uint32_t* __restrict__ counters, const float4* __restrict__ ray_o,
                                                   const float4* __restrict__ ray_d, const float4* __restrict__ state,
-                                                  uint4* __restrict__ trav) {
+                                                  uint4* __restrict__ trav, const SplitIO io) {
   const uint32_t n = counters[0];
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float4 o = ray_o[i], d = ray_d[i];
-    const uint4 tr = trav[i];
+    const uint4 tr = load_closest(trav, io, i);
     const RngKey key = key_of_slot(fp, __float_as_uint(state[i].w));
     Closest best{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)};
     int32_t mh = -1;
@@ -222,13 +226,13 @@ template <class M>
 __global__ void __launch_bounds__(kBlock) k_finish_hit(const DeviceScene S, const FrameParams fp, uint32_t bounce,
                                                        uint32_t* __restrict__ counters, const float4* __restrict__ ray_o,
                                                        const float4* __restrict__ ray_d, const float4* __restrict__ state,
-                                                       const uint4* __restrict__ trav, float4* __restrict__ hit0,
+                                                       const uint4* __restrict__ trav, const SplitIO io, float4* __restrict__ hit0,
                                                        float4* __restrict__ hit1, BinQueues bins) {
   const uint32_t n = counters[0];
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float4 o = ray_o[i], d = ray_d[i];
-    const uint4 tr = trav[i];
+    const uint4 tr = load_closest(trav, io, i);
     const RngKey key = key_of_slot(fp, __float_as_uint(state[i].w));
     HitOut h;
     finish_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, bounce,
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
                                                          uint32_t* __restrict__ counters, uint32_t* __restrict__ next_counters,
                                                          const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                          const float4* __restrict__ state, const uint4* __restrict__ trav,
-                                                         float4* __restrict__ hit0, float4* __restrict__ hit1, BinQueues bins,
+                                                         const SplitIO io, float4* __restrict__ hit0, float4* __restrict__ hit1, BinQueues bins,
                                                          float4* __restrict__ out_o, float4* __restrict__ out_d,
                                                          float4* __restrict__ out_state, uint32_t* __restrict__ sort_keys,
                                                          float4* __restrict__ radiance) {
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
     float4 no = make_float4(0, 0, 0, 0), nd = make_float4(0, 0, 0, 0), ns = make_float4(0, 0, 0, 0);
     if (i < n) {
       const float4 o = ray_o[i], d = ray_d[i];
-      const uint4 tr = trav[i];
+      const uint4 tr = load_closest(trav, io, i);
       const float4 st = state[i];
       const uint32_t slot = __float_as_uint(st.w);
       const RngKey key = key_of_slot(fp, slot);
@@ -369,7 +373,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
       out_o[dst] = no;
       out_d[dst] = nd;
       out_state[dst] = ns;
+#ifdef RT2_WITH_RAY_SORT
       if (sort_keys) sort_keys[dst] = ray_sort_key(S, make_f3(no), make_f3(nd));
+#endif
     }
     parity ^= 1;  // the next tile uses the other copy of s_off / s_base: no third barrier
   }
@@ -439,7 +445,9 @@ __global__ void __launch_bounds__(kBlock) k_shade_scatter(const DeviceScene S, c
     out_o[dst] = make_float4(h0.x, h0.y, h0.z, time);
     out_d[dst] = make_float4(dir.x, dir.y, dir.z, 0.0f);
     out_state[dst] = make_float4(st.x * att.x, st.y * att.y, st.z * att.z, st.w);
+#ifdef RT2_WITH_RAY_SORT
     if (sort_keys) sort_keys[dst] = ray_sort_key(S, make_f3(h0), dir);
+#endif
   }
 }
 
@@ -532,13 +540,13 @@ __global__ void k_batch_stats(const uint32_t* __restrict__ counters, uint32_t ma
 // Fixed-ray parity hook (rt2_intersect): the same traversal (k_traverse) followed by this record writer.
 template <class M>
 __global__ void __launch_bounds__(kBlock) k_finish_intersect(const DeviceScene S, const float4* __restrict__ ray_o,
-                                                             const float4* __restrict__ ray_d, const uint4* __restrict__ trav, uint32_t n,
-                                                             float tmin, int skip_media, uint32_t seed_lo, uint32_t seed_hi,
-                                                             rt2_hit* __restrict__ out) {
+                                                             const float4* __restrict__ ray_d, const uint4* __restrict__ trav,
+                                                             const SplitIO io, uint32_t n, float tmin, int skip_media, uint32_t seed_lo,
+                                                             uint32_t seed_hi, rt2_hit* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 o = ray_o[i], d = ray_d[i];
-  const uint4 tr = trav[i];
+  const uint4 tr = load_closest(trav, io, i);
   RngKey key{i, 0u, seed_lo, seed_hi};
   HitOut h;
   finish_hit<M>(S, make_f3(o), make_f3(d), o.w, tmin, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, 0,
@@ -553,15 +561,6 @@ __global__ void __launch_bounds__(kBlock) k_finish_intersect(const DeviceScene S
   r.front_face = h.front_face ? 1u : 0u;
   r.uv16 = (h.material < 0) ? 0u : pack_uv16(h.u, h.v);
   out[i] = r;
-}
-
-// k_traverse with caller-supplied interval and a plain count (rt2_intersect).
-template <class M>
-__global__ void __launch_bounds__(kBlock) k_traverse_rays(const DeviceScene S, uint32_t n, uint32_t* __restrict__ cursor,
-                                                          const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float tmin,
-                                                          float tmax, uint4* __restrict__ trav) {
-  TravCounters cnt;
-  traverse_queue<M, false, kFetchThreshold>(S, n, ray_o, ray_d, tmin, tmax, cursor, nullptr, trav, cnt);
 }
 
 }  // namespace rt2dev
@@ -597,9 +596,12 @@ struct Renderer::Impl {
   size_t cap_images{0}, cap_image_texels{0};
   void* d_flat_refs{nullptr};
   void* d_flat_offsets{nullptr};
-  void* d_flat_bounds{nullptr};
-  size_t cap_flat_refs{0}, cap_flat_offsets{0}, cap_flat_bounds{0};
+  void* d_inst_bounds{nullptr};
+  size_t cap_flat_refs{0}, cap_flat_offsets{0}, cap_inst_bounds{0};
   bool flat_mode{false};  // tiny scene: k_traverse_flat instead of the BVH walk
+  bool split_mode{false};  // instance split: k_traverse<kTravWorld> + k_traverse<kTravInst> (1..kMaxHoistedInstances instances)
+  SplitIO split{};         // entry queue / per-entry winner / per-ray merge slot (allocated in Resize when split_mode)
+  size_t split_capacity{0};  // entries the queue holds (= paths per batch x instances)
   bool split_media{false};  // media with multi-primitive boundaries: k_media pass + media-free fused kernel
   void* d_nodes4{nullptr};  // RT2_FLAG_WIDE_BVH: 4-wide quantised nodes collapsed from the device LBVH (rt_wide.cuh)
   size_t cap_nodes4{0};
@@ -631,7 +633,7 @@ struct Renderer::Impl {
   uchar4* rgba8{nullptr};
   unsigned long long* totals{nullptr};  // [0] rays [1] paths [2..5] work counters (box pairs, spheres, quads, instances)
   cudaStream_t stream{nullptr};
-  cudaEvent_t ev_start{nullptr}, ev_stop{nullptr};
+  cudaEvent_t ev_start{nullptr}, ev_stop{nullptr}, ev_done{nullptr};
   std::vector<cudaEvent_t> timing_events;  // start/stop pairs of rt2_update calls not yet folded into gpu_ms_total
   size_t timing_used{0};
   int grid_extend{0}, grid_stream{0};
@@ -644,8 +646,6 @@ struct Renderer::Impl {
   uint32_t* sort_hist{nullptr};
   uint32_t* sort_bin_base{nullptr};
   int grid_sort{0};
-  int fs_blocks{4};  // resident blocks per SM the fused kernel is compiled for (4: 64 registers, a few spills; measured +1-2 %)
-  int trav_blocks{4};
   int trav_max_steps{8};  // node steps per round of the while-while traversal (measured: +12 % on the 1M-sphere scene, +1 % on book 2)
   int trav_fetch_threshold{kFetchThreshold};
   bool fused{true};               // k_finish_shade instead of k_finish_hit + per-bin shade kernels
@@ -665,7 +665,7 @@ Renderer::~Renderer() {
   cudaSetDevice(cfg_.device);
   FreeState();
   Impl& m = *impl_;
-  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_flat_bounds, m.d_images, m.d_image_texels, m.d_nodes4};
+  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_inst_bounds, m.d_images, m.d_image_texels, m.d_nodes4};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.totals) cudaFree(m.totals);
@@ -674,6 +674,7 @@ Renderer::~Renderer() {
   FreeLbvhScratch(&m.lbvh_scratch);
   if (m.ev_start) cudaEventDestroy(m.ev_start);
   if (m.ev_stop) cudaEventDestroy(m.ev_stop);
+  if (m.ev_done) cudaEventDestroy(m.ev_done);
   for (cudaEvent_t e : m.prof_events) cudaEventDestroy(e);
   for (cudaEvent_t e : m.timing_events) cudaEventDestroy(e);
   if (m.stream) cudaStreamDestroy(m.stream);
@@ -690,6 +691,12 @@ void Renderer::FreeState() {
     if (b) cudaFree(b);
   if (m.bins.base) cudaFree(m.bins.base);
   m.bins.base = nullptr;
+  if (m.split.entries) cudaFree(m.split.entries);
+  if (m.split.entry_prim) cudaFree(m.split.entry_prim);
+  if (m.split.inst_best) cudaFree(m.split.inst_best);
+  m.split = SplitIO{};
+  m.split_capacity = 0;
+  state_ok_ = false;
   m.ray_o[0] = m.ray_o[1] = m.ray_d[0] = m.ray_d[1] = m.state[0] = m.state[1] = m.hit0 = m.hit1 = nullptr;
   m.trav = nullptr;
   m.counters = nullptr;
@@ -721,27 +728,27 @@ int Renderer::Init(const HostScene& scene, const rt2_config& cfg) {
   if (cfg_.frame_stride < 1) cfg_.frame_stride = 1;
   // persistent grids: resident blocks per SM x SM count
   int occ = 0;
-  if (const char* e = getenv("RT2_FS_BLOCKS")) m.fs_blocks = atoi(e);
-  if (const char* e = getenv("RT2_TRAV_STEPS")) m.trav_max_steps = atoi(e);
-  if (const char* e = getenv("RT2_TRAV_FETCH")) m.trav_fetch_threshold = atoi(e);
+  m.trav_max_steps = static_cast<int>(TuneInt("RT2_TRAV_STEPS", m.trav_max_steps));
+  m.trav_fetch_threshold = static_cast<int>(TuneInt("RT2_TRAV_FETCH", m.trav_fetch_threshold));
   if (cfg_.flags & RT2_FLAG_FAST_MATH) {
-    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<FastMath, false>, kBlock, 0));
+    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<FastMath, false, kTravInline>, kBlock, 0));
   } else {
-    if (const char* e = getenv("RT2_TRAV_BLOCKS")) m.trav_blocks = atoi(e);
-    if (m.trav_blocks == 5) RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false, 0, 5>, kBlock, 0));
-    else if (m.trav_blocks == 6) RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false, 0, 6>, kBlock, 0));
-    else RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false>, kBlock, 0));
+    RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<ExactMath, false, kTravInline>, kBlock, 0));
   }
   if (occ < 1) occ = 1;
   m.grid_extend = sm_count_ * occ;
   m.grid_stream = sm_count_ * 8;
   m.grid_sort = sm_count_ * 4;
   m.sort_enabled = (cfg_.flags & RT2_FLAG_SORT_RAYS) != 0;
-  if (const char* e = getenv("RT2_SORT")) m.sort_enabled = atoi(e) != 0;
-  if (const char* e = getenv("RT2_SORT_MIN")) m.sort_min_rays = static_cast<uint32_t>(atol(e));
-  if (const char* e = getenv("RT2_SORT_MAXB")) m.sort_max_bounce = static_cast<uint32_t>(atol(e));
+#ifndef RT2_WITH_RAY_SORT
+  if (m.sort_enabled) {
+    err_ = "RT2_FLAG_SORT_RAYS: the ray sort measured as a net loss and is only compiled into EXPERIMENTS builds";
+    return RT2_ERR_UNSUPPORTED;
+  }
+#endif
+  m.sort_min_rays = static_cast<uint32_t>(TuneInt("RT2_SORT_MIN", m.sort_min_rays));
+  m.sort_max_bounce = static_cast<uint32_t>(TuneInt("RT2_SORT_MAXB", m.sort_max_bounce));
   m.fused = (cfg_.flags & RT2_FLAG_NO_FUSED_SHADE) == 0;
-  if (const char* e = getenv("RT2_FUSED")) m.fused = atoi(e) != 0;
   int rc = UploadScene(scene);
   if (rc != RT2_OK) return rc;
   int w = cfg.width > 0 ? cfg.width : scene.width;
@@ -896,6 +903,8 @@ int Renderer::UploadScene(const HostScene& scene) {
     }
     n_node_pairs_ = static_cast<uint32_t>(scene.nodes.size() / 2);
     n_prim_refs_ = static_cast<uint32_t>(scene.prim_refs.size());
+    world_tree_ok_ = scene.has_world_tlas;
+    world_root_ = scene.tlas_world_root;
     bvh_build_ms_ = 0;
     m.wide_mode = false;
     if (cfg_.flags & RT2_FLAG_WIDE_BVH) {
@@ -966,31 +975,35 @@ int Renderer::UploadScene(const HostScene& scene) {
   }
   m.split_media = false;
   for (const rt2_medium& md : scene.media) m.split_media = m.split_media || md.boundary_count > 1;
-  if (const char* e = getenv("RT2_SPLIT_MEDIA")) m.split_media = !scene.media.empty() && atoi(e) != 0;
+  if (TuneInt("RT2_SPLIT_MEDIA", -1) >= 0) m.split_media = !scene.media.empty() && TuneInt("RT2_SPLIT_MEDIA", 0) != 0;
+  // conservative world boxes of the instances (flat mode and instance split)
+  d.inst_bounds = nullptr;
+  if (!scene.inst_bounds.empty()) {
+    if (scene.inst_bounds.size() != scene.instances.size() * 8) {
+      err_ = "scene carries inconsistent instance bounds";
+      return RT2_ERR_STATE;
+    }
+    rc = UploadBuf(m, &m.d_inst_bounds, &m.cap_inst_bounds, scene.inst_bounds, &err_);
+    if (rc != RT2_OK) return rc;
+    d.inst_bounds = static_cast<const float4*>(m.d_inst_bounds);
+  }
   // flat mode: list every leaf primitive by space when the scene is tiny
   m.flat_mode = false;
   d.flat_refs = nullptr;
   d.flat_offsets = nullptr;
-  d.flat_inst_bounds = nullptr;
-  uint32_t flat_max = kFlatMaxPrims;
-  if (const char* e = getenv("RT2_FLAT_MAX")) flat_max = static_cast<uint32_t>(atol(e));
-  if (const char* e = getenv("RT2_FLAT")) flat_max = atoi(e) ? flat_max : 0u;
+  uint32_t flat_max = static_cast<uint32_t>(TuneInt("RT2_FLAT_MAX", kFlatMaxPrims));
+  if (TuneInt("RT2_FLAT", 1) == 0) flat_max = 0u;
   // (an explicit RT2_FLAG_GPU_LBVH asks for the device-built trees: keep the BVH walk)
-  if (!gpu_bvh && flat_max > 0 && scene.tree_prims.size() == scene.instances.size() + 1) {
+  if (!gpu_bvh && flat_max > 0 && scene.tree_prims.size() == scene.instances.size() + 1 &&
+      (scene.instances.empty() || d.inst_bounds != nullptr)) {
     std::vector<uint32_t> refs, offsets;
-    std::vector<float> bounds(scene.instances.size() * 8, 0.0f);
     bool ok = true;
     offsets.push_back(0);
     for (const BuildPrim& bp : scene.tree_prims[0]) {
       if (RT2_PRIM_TYPE(bp.ref) == RT2_PRIM_INSTANCE) {
-        const uint32_t j = RT2_PRIM_INDEX(bp.ref);
-        if (j >= scene.instances.size()) {
+        if (RT2_PRIM_INDEX(bp.ref) >= scene.instances.size()) {
           ok = false;
           break;
-        }
-        for (int k = 0; k < 3; k++) {
-          bounds[8 * j + k] = bp.bmin[k];
-          bounds[8 * j + 4 + k] = bp.bmax[k];
         }
       } else {
         refs.push_back(bp.ref);
@@ -1009,16 +1022,24 @@ int Renderer::UploadScene(const HostScene& scene) {
       if (rc != RT2_OK) return rc;
       rc = UploadBuf(m, &m.d_flat_offsets, &m.cap_flat_offsets, offsets, &err_);
       if (rc != RT2_OK) return rc;
-      rc = UploadBuf(m, &m.d_flat_bounds, &m.cap_flat_bounds, bounds, &err_);
-      if (rc != RT2_OK) return rc;
       RT2_CUDA(cudaStreamSynchronize(m.stream));  // the host vectors are temporaries
       d.flat_refs = static_cast<const uint32_t*>(m.d_flat_refs);
       d.flat_offsets = static_cast<const uint32_t*>(m.d_flat_offsets);
-      d.flat_inst_bounds = static_cast<const float4*>(m.d_flat_bounds);
       m.flat_mode = true;
     }
   }
+  // instance split: the few instances are hoisted out of the world tree (rt_trace.cuh, kTravWorld / kTravInst)
+  const bool was_split = m.split_mode;
+  m.split_mode = !m.flat_mode && !m.wide_mode && !(cfg_.flags & RT2_FLAG_NO_INSTANCE_SPLIT) && world_tree_ok_ &&
+                 !scene.instances.empty() && scene.instances.size() <= kMaxHoistedInstances && d.inst_bounds != nullptr;
+  d.n_hoisted = m.split_mode ? static_cast<uint32_t>(scene.instances.size()) : 0u;
+  d.tlas_world_root = m.split_mode ? world_root_ : d.tlas_root;
+  if (m.split_mode && (!was_split || !m.split.entries) && width_ > 0) {
+    rc = AllocSplitState();  // a re-upload switched the renderer into split mode after Resize
+    if (rc != RT2_OK) return rc;
+  }
   cam_params_ = scene.cam;
+  n_textures_ = static_cast<uint32_t>(scene.textures.size());
   RT2_CUDA(cudaStreamSynchronize(m.stream));  // the staging arena (and any temporary above) may be reused from here on
   return RT2_OK;
 }
@@ -1040,19 +1061,32 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
     md.boundary_first = first;
   }
   std::vector<rt2_instance> instances = scene.instances;
-  const size_t n_trees = scene.tree_prims.size();
+  // trees: [0] world TLAS (instances as leaves), [1 + i] BLAS of instance i, and — for the instance split — one more
+  // world tree over the surfaces only
+  std::vector<const std::vector<BuildPrim>*> trees;
+  for (const std::vector<BuildPrim>& tp : scene.tree_prims) trees.push_back(&tp);
+  std::vector<BuildPrim> surfaces;
+  const bool want_world_tree = !scene.instances.empty() && scene.instances.size() <= kMaxHoistedInstances;
+  if (want_world_tree) {
+    for (const BuildPrim& bp : scene.tree_prims[0])
+      if (RT2_PRIM_TYPE(bp.ref) != RT2_PRIM_INSTANCE) surfaces.push_back(bp);
+    trees.push_back(&surfaces);
+  }
+  const size_t n_trees = trees.size();
   std::vector<uint32_t> pair_base(n_trees), ref_base(n_trees);
   uint64_t pairs = 0, refs = prefix.size();
   size_t max_n = 0;
   for (size_t k = 0; k < n_trees; k++) {
-    const size_t n = scene.tree_prims[k].size();
+    const size_t n = trees[k]->size();
     pair_base[k] = static_cast<uint32_t>(pairs);
     ref_base[k] = static_cast<uint32_t>(refs);
     pairs += n > 1 ? n - 1 : 1;
     refs += n;
     max_n = n > max_n ? n : max_n;
-    if (k > 0) instances[k - 1].blas_root = pair_base[k];
+    if (k > 0 && k <= scene.instances.size()) instances[k - 1].blas_root = pair_base[k];
   }
+  world_tree_ok_ = want_world_tree;
+  world_root_ = want_world_tree ? pair_base[n_trees - 1] : 0u;
   if (pairs >= 0x7FFFFFF0ull || refs >= 0x03FFFFFFull) {
     err_ = "scene too large for the 26-bit primitive / 31-bit node index fields";
     return RT2_ERR_UNSUPPORTED;
@@ -1081,7 +1115,7 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
   if (!prefix.empty()) RT2_CUDA(cudaMemcpyAsync(m.d_prim_refs, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, m.stream));
   RT2_CUDA(cudaEventRecord(m.ev_start, m.stream));
   for (size_t k = 0; k < n_trees; k++) {
-    const std::vector<BuildPrim>& tp = scene.tree_prims[k];
+    const std::vector<BuildPrim>& tp = *trees[k];
     if (!tp.empty()) {
       RT2_CUDA(cudaMemcpyAsync(m.d_build_prims, tp.data(), tp.size() * sizeof(BuildPrim), cudaMemcpyHostToDevice, m.stream));
     }
@@ -1147,6 +1181,28 @@ int Renderer::ReadBvh(rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs
   return RT2_OK;
 }
 
+// Entry queue of the instance split: every ray can produce one entry per hoisted instance.
+int Renderer::AllocSplitState() {
+  Impl& m = *impl_;
+  if (m.split.entries) cudaFree(m.split.entries);
+  if (m.split.entry_prim) cudaFree(m.split.entry_prim);
+  if (m.split.inst_best) cudaFree(m.split.inst_best);
+  m.split = SplitIO{};
+  m.split_capacity = 0;
+  const size_t N = static_cast<size_t>(width_) * height_ * static_cast<size_t>(frames_per_batch_);
+  const size_t cap = N * m.ds.n_hoisted;
+  if (cap == 0) return RT2_OK;
+  if (cap >= 0xFFFFFFF0ull) {
+    err_ = "batch too large for the instance-split entry queue";
+    return RT2_ERR_INVALID_ARG;
+  }
+  RT2_CUDA(cudaMalloc(&m.split.entries, cap * sizeof(uint2)));
+  RT2_CUDA(cudaMalloc(&m.split.entry_prim, cap * sizeof(uint32_t)));
+  RT2_CUDA(cudaMalloc(&m.split.inst_best, N * sizeof(unsigned long long)));
+  m.split_capacity = cap;
+  return RT2_OK;
+}
+
 int Renderer::Resize(int w, int h) {
   Impl& m = *impl_;
   if (w <= 0 || h <= 0) {
@@ -1156,6 +1212,7 @@ int Renderer::Resize(int w, int h) {
   RT2_CUDA(cudaSetDevice(cfg_.device));
   RT2_CUDA(cudaStreamSynchronize(m.stream));
   FreeState();
+  pending_frames_ = 0;
   width_ = w;
   height_ = h;
   // camera for the new dims (Camera::SetDims + Update)
@@ -1165,6 +1222,22 @@ int Renderer::Resize(int w, int h) {
   tmp.height = h;
   tmp.UpdateCamera();
   camera_ = tmp.camera_block;
+  int rc = AllocState();
+  if (rc != RT2_OK) {
+    // a failed allocation (e.g. out of memory at a huge size) must not leave a half-built renderer behind: every later
+    // call reports RT2_ERR_STATE until a Resize succeeds
+    FreeState();
+    cudaGetLastError();
+    width_ = height_ = 0;
+    return rc;
+  }
+  state_ok_ = true;
+  return Reset();
+}
+
+int Renderer::AllocState() {
+  Impl& m = *impl_;
+  const int w = width_, h = height_;
   const size_t P = static_cast<size_t>(w) * h;
   int F = cfg_.frames_per_batch;
   if (F <= 0) {
@@ -1204,6 +1277,7 @@ int Renderer::Resize(int w, int h) {
   if (cfg_.flags & RT2_FLAG_MOMENTS) RT2_CUDA(cudaMalloc(&m.accum_sq, P * sizeof(float4)));
   RT2_CUDA(cudaMalloc(&m.mean_rgb, P * 3 * sizeof(float)));
   RT2_CUDA(cudaMalloc(&m.rgba8, P * sizeof(uchar4)));
+#ifdef RT2_WITH_RAY_SORT
   if (m.sort_enabled) {
     for (int i = 0; i < 2; i++) {
       RT2_CUDA(cudaMalloc(&m.sort_keys[i], N * sizeof(uint32_t)));
@@ -1212,12 +1286,16 @@ int Renderer::Resize(int w, int h) {
     RT2_CUDA(cudaMalloc(&m.sort_hist, static_cast<size_t>(m.grid_sort) * kSortBins * sizeof(uint32_t)));
     RT2_CUDA(cudaMalloc(&m.sort_bin_base, kSortBins * sizeof(uint32_t)));
   }
-  return Reset();
+#endif
+  if (m.split_mode) return AllocSplitState();
+  return RT2_OK;
 }
 
 int Renderer::Reset() {
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (!state_ok_) return NoState();
+  pending_frames_ = 0;  // frames requested but not yet traced are dropped with the accumulators (RayTracer.cpp:49-53)
   const size_t P = static_cast<size_t>(width_) * height_;
   RT2_CUDA(cudaMemsetAsync(m.accum, 0, P * sizeof(float4), m.stream));
   if (m.accum_sq) RT2_CUDA(cudaMemsetAsync(m.accum_sq, 0, P * sizeof(float4), m.stream));
@@ -1226,6 +1304,61 @@ int Renderer::Reset() {
   gpu_ms_total_ = 0;
   for (double& v : prof_ms_) v = 0;
   return RT2_OK;
+}
+
+// One extend stage = closest surface of every queued ray, by whichever traversal the scene uses.
+struct ExtendArgs {
+  const uint32_t* n_ptr;   // device-resident ray count, or nullptr: n_fixed
+  uint32_t n_fixed;
+  uint32_t* cursor;        // fetch cursor of the ray queue
+  uint32_t* entry_count;   // instance split: entry counter and fetch cursor of this stage
+  uint32_t* entry_cursor;
+  const float4* ray_o;
+  const float4* ray_d;
+  float tmin, tmax;
+  const uint32_t* order;
+  uint32_t sort_min_rays;
+  uint4* trav;
+  SplitIO io;
+  int grid;                // persistent grid of the BVH walks
+  int grid_flat;           // grid of the flat kernel
+};
+
+template <class M, bool kCount>
+static void LaunchExtendT(Renderer::Impl& m, const ExtendArgs& a, uint64_t* launches) {
+  if (m.wide_mode) {
+    k_traverse_wide<M, kCount><<<a.grid, kBlock, 0, m.stream>>>(m.ds, m.wide, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
+                                                                a.trav, m.totals, m.trav_max_steps);
+    (*launches)++;
+  } else if (m.flat_mode) {
+    k_traverse_flat<M><<<a.grid_flat, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.ray_o, a.ray_d, a.tmin, a.tmax, a.trav);
+    (*launches)++;
+  } else if (m.split_mode) {
+    SplitIO io = a.io;
+    io.entry_count = a.entry_count;
+    k_traverse<M, kCount, kTravWorld><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
+                                                                       a.order, a.sort_min_rays, a.trav, io, m.totals, m.trav_max_steps,
+                                                                       m.trav_fetch_threshold);
+    k_traverse<M, kCount, kTravInst><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.entry_count, 0u, a.entry_cursor, a.ray_o, a.ray_d, a.tmin,
+                                                                      a.tmax, nullptr, 0u, a.trav, io, m.totals, m.trav_max_steps,
+                                                                      m.trav_fetch_threshold);
+    *launches += 2;
+  } else {
+    k_traverse<M, kCount, kTravInline><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
+                                                                        a.order, a.sort_min_rays, a.trav, SplitIO{}, m.totals,
+                                                                        m.trav_max_steps, m.trav_fetch_threshold);
+    (*launches)++;
+  }
+}
+
+static void LaunchExtend(Renderer::Impl& m, const ExtendArgs& a, bool exact, bool count, uint64_t* launches) {
+  if (exact) {
+    if (count) LaunchExtendT<ExactMath, true>(m, a, launches);
+    else LaunchExtendT<ExactMath, false>(m, a, launches);
+  } else {
+    if (count) LaunchExtendT<FastMath, true>(m, a, launches);
+    else LaunchExtendT<FastMath, false>(m, a, launches);
+  }
 }
 
 template <int kType, int kBin>
@@ -1288,6 +1421,7 @@ int Renderer::RenderBatch(uint32_t n_frames) {
     const bool sorted = m.sort_enabled && !m.flat_mode && b >= 1 && b <= m.sort_max_bounce;  // the flat extend kernel has no use for an order
     const bool sort_next = m.sort_enabled && !m.flat_mode && b + 1 <= m.sort_max_bounce;
     const uint32_t* order = nullptr;
+#ifdef RT2_WITH_RAY_SORT
     if (sorted) {
       prof(5);
       const uint32_t smin = m.sort_min_rays;
@@ -1302,53 +1436,49 @@ int Renderer::RenderBatch(uint32_t n_frames) {
       launches_ += 6;
       order = m.sort_vals[0];
     }
+#else
+    (void)sorted;
+#endif
     prof(1);
-    unsigned long long* work = m.totals + 2;
-    const uint32_t smin = m.sort_min_rays;
-    if (m.wide_mode) {
-      if (exact) {
-        if (profiling_) k_traverse_wide<ExactMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, m.wide, ctr, 0u, nullptr, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav, work, m.trav_max_steps);
-        else k_traverse_wide<ExactMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, m.wide, ctr, 0u, nullptr, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav, work, m.trav_max_steps);
-      } else {
-        if (profiling_) k_traverse_wide<FastMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, m.wide, ctr, 0u, nullptr, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav, work, m.trav_max_steps);
-        else k_traverse_wide<FastMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, m.wide, ctr, 0u, nullptr, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav, work, m.trav_max_steps);
-      }
-    } else if (m.flat_mode) {
-      if (exact) k_traverse_flat<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, 0u, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav);
-      else k_traverse_flat<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, ctr, 0u, m.ray_o[in], m.ray_d[in], 0.001f, kFltMax, m.trav);
-    } else if (exact) {
-      if (profiling_) k_traverse<ExactMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
-      else if (m.trav_blocks == 5) k_traverse<ExactMath, false, 0, 5><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
-      else if (m.trav_blocks == 6) k_traverse<ExactMath, false, 0, 6><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
-      else k_traverse<ExactMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
-    } else {
-      if (profiling_) k_traverse<FastMath, true><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
-      else k_traverse<FastMath, false><<<m.grid_extend, kBlock, 0, m.stream>>>(m.ds, ctr, m.ray_o[in], m.ray_d[in], order, smin, m.trav, work, m.trav_max_steps, m.trav_fetch_threshold);
+    {
+      ExtendArgs ea{};
+      ea.n_ptr = ctr;
+      ea.cursor = ctr + 7;
+      ea.entry_count = ctr + 8;
+      ea.entry_cursor = ctr + 9;
+      ea.ray_o = m.ray_o[in];
+      ea.ray_d = m.ray_d[in];
+      ea.tmin = 0.001f;  // Interval{0.001, kInfinity} (RayTracer.cpp:25)
+      ea.tmax = kFltMax;
+      ea.order = order;
+      ea.sort_min_rays = m.sort_min_rays;
+      ea.trav = m.trav;
+      ea.io = m.split;
+      ea.grid = m.grid_extend;
+      ea.grid_flat = m.grid_stream;
+      LaunchExtend(m, ea, exact, profiling_, &launches_);
     }
     prof(3);
     const bool last = (b + 1 == max_depth);  // RayColor(depth <= 0) returns black: nothing to scatter into
     uint32_t* keys = (sort_next && !last) ? m.sort_keys[0] : nullptr;
+    const SplitIO io = m.split;  // all-null unless the instance split is active (then load_closest merges the entries)
     if (m.fused) {
       // finish + inline shade; only noise-textured materials go through the bins
-      if (exact && m.fs_blocks == 3) {
-        k_finish_shade<ExactMath, 3><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
-                                                                             m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
-                                                                             m.ray_d[out], m.state[out], keys, m.radiance);
-      } else if (exact && (m.ds.n_media == 0 || m.split_media)) {
+      if (exact && (m.ds.n_media == 0 || m.split_media)) {
         if (m.split_media) {
-          k_media<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav);
+          k_media<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, io);
           launches_++;
         }
         k_finish_shade<ExactMath, 4, false><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
-                                                                                   m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
+                                                                                   m.state[in], m.trav, io, m.hit0, m.hit1, m.bins, m.ray_o[out],
                                                                                    m.ray_d[out], m.state[out], keys, m.radiance);
       } else if (exact) {
         k_finish_shade<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
-                                                                          m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
+                                                                          m.state[in], m.trav, io, m.hit0, m.hit1, m.bins, m.ray_o[out],
                                                                           m.ray_d[out], m.state[out], keys, m.radiance);
       } else {
         k_finish_shade<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
-                                                                         m.state[in], m.trav, m.hit0, m.hit1, m.bins, m.ray_o[out],
+                                                                         m.state[in], m.trav, io, m.hit0, m.hit1, m.bins, m.ray_o[out],
                                                                          m.ray_d[out], m.state[out], keys, m.radiance);
       }
       launches_++;
@@ -1364,11 +1494,11 @@ int Renderer::RenderBatch(uint32_t n_frames) {
       }
     } else {
       if (exact) {
-        k_finish_hit<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, m.hit0,
-                                                                        m.hit1, m.bins);
+        k_finish_hit<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, io,
+                                                                        m.hit0, m.hit1, m.bins);
       } else {
-        k_finish_hit<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, m.hit0,
-                                                                       m.hit1, m.bins);
+        k_finish_hit<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, io,
+                                                                       m.hit0, m.hit1, m.bins);
       }
       launches_++;
       prof(2);
@@ -1403,10 +1533,39 @@ int Renderer::RenderBatch(uint32_t n_frames) {
   return RT2_OK;
 }
 
+int Renderer::NoState() {
+  err_ = "the renderer has no frame buffers (the last rt2_resize failed): resize it first";
+  return RT2_ERR_STATE;
+}
+
+// n x RayTracer::Update (RayTracer.cpp:55-70).  The reference's app calls Update once per sample (App.cpp:244-246); tracing one
+// 600 x 600 frame per call would launch ~150 kernels over 360 k paths, so frames are collected until a wavefront batch is
+// full and traced then — or at the next call that needs them (Flush).  FrameIdx() counts traced + pending frames, the
+// stratum and Philox counters of a frame depend only on its index, so the image is the same as with eager tracing.
 int Renderer::Update(uint32_t n_frames) {
+  if (!state_ok_) return NoState();
+  pending_frames_ += n_frames;
+  while (pending_frames_ >= static_cast<uint64_t>(frames_per_batch_)) {
+    int rc = TraceFrames(static_cast<uint32_t>(frames_per_batch_));
+    if (rc != RT2_OK) return rc;
+  }
+  return RT2_OK;
+}
+
+int Renderer::Flush() {
+  if (!state_ok_) return pending_frames_ ? NoState() : RT2_OK;
+  while (pending_frames_ > 0) {
+    const uint64_t f = pending_frames_ < static_cast<uint64_t>(frames_per_batch_) ? pending_frames_ : static_cast<uint64_t>(frames_per_batch_);
+    int rc = TraceFrames(static_cast<uint32_t>(f));
+    if (rc != RT2_OK) return rc;
+  }
+  return RT2_OK;
+}
+
+int Renderer::TraceFrames(uint32_t f) {
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
-  // one CUDA-event pair per call; folded into gpu_ms_total at the next synchronisation
+  // one CUDA-event pair per batch; folded into gpu_ms_total at the next synchronisation
   if (m.timing_used + 2 > m.timing_events.size()) {
     for (int k = 0; k < 2; k++) {
       cudaEvent_t e;
@@ -1417,13 +1576,10 @@ int Renderer::Update(uint32_t n_frames) {
   cudaEvent_t ev_a = m.timing_events[m.timing_used], ev_b = m.timing_events[m.timing_used + 1];
   m.timing_used += 2;
   RT2_CUDA(cudaEventRecord(ev_a, m.stream));
-  while (n_frames > 0) {
-    uint32_t f = n_frames < static_cast<uint32_t>(frames_per_batch_) ? n_frames : static_cast<uint32_t>(frames_per_batch_);
-    int rc = RenderBatch(f);
-    if (rc != RT2_OK) return rc;
-    frame_idx_ += f;
-    n_frames -= f;
-  }
+  int rc = RenderBatch(f);
+  if (rc != RT2_OK) return rc;
+  frame_idx_ += f;
+  pending_frames_ -= f;
   RT2_CUDA(cudaEventRecord(ev_b, m.stream));
   timing_pending_ = true;
   return RT2_OK;
@@ -1432,6 +1588,8 @@ int Renderer::Update(uint32_t n_frames) {
 int Renderer::Synchronize() {
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
+  int rc = Flush();
+  if (rc != RT2_OK) return rc;
   RT2_CUDA(cudaStreamSynchronize(m.stream));
   if (timing_pending_) {
     for (size_t i = 0; i + 1 < m.timing_used; i += 2) {
@@ -1444,9 +1602,26 @@ int Renderer::Synchronize() {
   return RT2_OK;
 }
 
+// A traversal that ran out of stack dropped a sub-tree: the image may miss hits.  Reported by every read-out instead of
+// returning a silently wrong image (never expected: the builders bound the depth of every tree).
+int Renderer::CheckOverflow() {
+  Impl& m = *impl_;
+  unsigned long long ov = 0;
+  RT2_CUDA(cudaMemcpy(&ov, m.totals + 6, sizeof(ov), cudaMemcpyDeviceToHost));
+  if (ov != 0) {
+    err_ = "BVH traversal stack overflow in " + std::to_string(ov) + " warp(s): a tree is deeper than the " + std::to_string(kStackSize) +
+           "-entry stack, the image is incomplete";
+    return RT2_ERR_STATE;
+  }
+  return RT2_OK;
+}
+
 int Renderer::ReadMean(float* dst) {
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (!state_ok_) return NoState();
+  int rcf = Flush();
+  if (rcf != RT2_OK) return rcf;
   const uint32_t P = static_cast<uint32_t>(width_) * height_;
   // accum / frame_idx_ — with no frames the reference divides by zero (NaN); we do the same
   k_resolve<<<m.grid_stream, kBlock, 0, m.stream>>>(P, static_cast<float>(frame_idx_), m.accum, m.mean_rgb, nullptr);
@@ -1457,16 +1632,21 @@ int Renderer::ReadMean(float* dst) {
   if (m.h_stage_cap >= bytes) {  // D2H into page-locked memory, then a host copy into the caller's buffer
     RT2_CUDA(cudaMemcpyAsync(m.h_stage, m.mean_rgb, bytes, cudaMemcpyDeviceToHost, m.stream));
     rc = Synchronize();
+    if (rc == RT2_OK) rc = CheckOverflow();
     if (rc == RT2_OK) std::memcpy(dst, m.h_stage, bytes);
     return rc;
   }
   RT2_CUDA(cudaMemcpyAsync(dst, m.mean_rgb, bytes, cudaMemcpyDeviceToHost, m.stream));
-  return Synchronize();
+  rc = Synchronize();
+  return rc == RT2_OK ? CheckOverflow() : rc;
 }
 
 int Renderer::ReadRGBA8(uint8_t* dst) {
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (!state_ok_) return NoState();
+  int rcf = Flush();
+  if (rcf != RT2_OK) return rcf;
   const uint32_t P = static_cast<uint32_t>(width_) * height_;
   k_resolve<<<m.grid_stream, kBlock, 0, m.stream>>>(P, static_cast<float>(frame_idx_), m.accum, nullptr, m.rgba8);
   launches_++;
@@ -1476,17 +1656,21 @@ int Renderer::ReadRGBA8(uint8_t* dst) {
   if (m.h_stage_cap >= bytes) {
     RT2_CUDA(cudaMemcpyAsync(m.h_stage, m.rgba8, bytes, cudaMemcpyDeviceToHost, m.stream));
     rc = Synchronize();
+    if (rc == RT2_OK) rc = CheckOverflow();
     if (rc == RT2_OK) std::memcpy(dst, m.h_stage, bytes);
     return rc;
   }
   RT2_CUDA(cudaMemcpyAsync(dst, m.rgba8, bytes, cudaMemcpyDeviceToHost, m.stream));
-  return Synchronize();
+  rc = Synchronize();
+  return rc == RT2_OK ? CheckOverflow() : rc;
 }
 
 int Renderer::ReadAccum(float* sum, float* sumsq) {
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (!state_ok_) return NoState();
   int rc = Synchronize();
+  if (rc == RT2_OK) rc = CheckOverflow();
   if (rc != RT2_OK) return rc;
   const size_t P = static_cast<size_t>(width_) * height_;
   std::vector<float4> tmp(P);
@@ -1518,6 +1702,8 @@ int Renderer::ReadAccum(float* sum, float* sumsq) {
 int Renderer::WriteAccum(const float* sum, const float* sumsq, uint64_t frames) {
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (!state_ok_) return NoState();
+  pending_frames_ = 0;  // the restored accumulators replace whatever was requested before
   int rc = Synchronize();
   if (rc != RT2_OK) return rc;
   const size_t P = static_cast<size_t>(width_) * height_;
@@ -1568,20 +1754,22 @@ int Renderer::ResolvePeers(const uint8_t* handles, uint32_t n_ranks, uint32_t se
                            uint8_t* dst_rgba8) {
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (!state_ok_) return NoState();
   if (n_ranks < 1 || n_ranks > static_cast<uint32_t>(kMaxPeers) || self_rank >= n_ranks || (n_ranks > 1 && !handles)) {
     err_ = "rt2_resolve_peers: bad rank arguments";
     return RT2_ERR_INVALID_ARG;
   }
+  int rc = Flush();
+  if (rc != RT2_OK) return rc;
   const uint32_t P = static_cast<uint32_t>(width_) * height_;
   const size_t b_mean = static_cast<size_t>(P) * 3 * sizeof(float), b_rgba = static_cast<size_t>(P) * 4;
   // Every allocation this call needs is made BEFORE the peers are mapped, and the mappings are closed before returning:
   // on the B200 boxes a cudaMallocHost issued while a lazily-enabled IPC mapping was open was handed the mapping's own
   // virtual address (measured: the second read-out then read the staging buffer instead of the peer), so no mapping
   // outlives the call.
-  int rc = EnsureStage(m, b_mean + b_rgba, &err_);
+  rc = EnsureStage(m, b_mean + b_rgba, &err_);
   if (rc != RT2_OK) return rc;
-  const bool staged = m.h_stage_cap >= b_mean + b_rgba;
-  PeerAccums pa{};
+  const void* ptrs[kMaxPeers];
   void* opened[kMaxPeers];
   int n_opened = 0;
   auto close_all = [&]() {
@@ -1590,7 +1778,7 @@ int Renderer::ResolvePeers(const uint8_t* handles, uint32_t n_ranks, uint32_t se
   };
   for (uint32_t r = 0; r < n_ranks; r++) {
     if (r == self_rank) {
-      pa.p[r] = m.accum;
+      ptrs[r] = m.accum;
       continue;
     }
     const uint8_t* hr = handles + static_cast<size_t>(RT2_IPC_HANDLE_BYTES) * r;
@@ -1606,9 +1794,31 @@ int Renderer::ResolvePeers(const uint8_t* handles, uint32_t n_ranks, uint32_t se
       return RT2_ERR_CUDA;
     }
     opened[n_opened++] = mapped;
-    pa.p[r] = reinterpret_cast<const float4*>(static_cast<const char*>(mapped) + offset);
+    ptrs[r] = static_cast<const char*>(mapped) + offset;
   }
-  k_resolve_peers<<<m.grid_stream, kBlock, 0, m.stream>>>(P, static_cast<float>(total_frames), pa, static_cast<int>(n_ranks),
+  rc = ResolvePointers(ptrs, n_ranks, total_frames, dst_mean, dst_rgba8);
+  close_all();
+  return rc;
+}
+
+// Sum of `n` accumulators (W*H float4 each, any device this one can address: own HBM, peer HBM over NVLink) in the order
+// given, divided by total_frames: mean and / or RGBA8 preview, one kernel on this renderer's stream, then the read-back.
+int Renderer::ResolvePointers(const void* const* accums, uint32_t n, uint64_t total_frames, float* dst_mean, uint8_t* dst_rgba8) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (!state_ok_) return NoState();
+  if (n < 1 || n > static_cast<uint32_t>(kMaxPeers)) {
+    err_ = "resolve: between 1 and " + std::to_string(kMaxPeers) + " accumulators";
+    return RT2_ERR_INVALID_ARG;
+  }
+  const uint32_t P = static_cast<uint32_t>(width_) * height_;
+  const size_t b_mean = static_cast<size_t>(P) * 3 * sizeof(float), b_rgba = static_cast<size_t>(P) * 4;
+  int rc = EnsureStage(m, b_mean + b_rgba, &err_);
+  if (rc != RT2_OK) return rc;
+  const bool staged = m.h_stage_cap >= b_mean + b_rgba;
+  PeerAccums pa{};
+  for (uint32_t r = 0; r < n; r++) pa.p[r] = static_cast<const float4*>(accums[r]);
+  k_resolve_peers<<<m.grid_stream, kBlock, 0, m.stream>>>(P, static_cast<float>(total_frames), pa, static_cast<int>(n),
                                                           dst_mean ? m.mean_rgb : nullptr, dst_rgba8 ? m.rgba8 : nullptr);
   launches_++;
   cudaError_t e = cudaSuccess;
@@ -1616,8 +1826,8 @@ int Renderer::ResolvePeers(const uint8_t* handles, uint32_t n_ranks, uint32_t se
   if (e == cudaSuccess && dst_rgba8)
     e = cudaMemcpyAsync(staged ? static_cast<void*>(m.h_stage + b_mean) : dst_rgba8, m.rgba8, b_rgba, cudaMemcpyDeviceToHost, m.stream);
   rc = (e == cudaSuccess) ? Synchronize() : RT2_ERR_CUDA;
-  if (e != cudaSuccess) err_ = std::string("rt2_resolve_peers copy failed: ") + cudaGetErrorString(e);
-  close_all();
+  if (e != cudaSuccess) err_ = std::string("resolve: copy failed: ") + cudaGetErrorString(e);
+  if (rc == RT2_OK) rc = CheckOverflow();
   if (rc == RT2_OK && staged) {
     if (dst_mean) std::memcpy(dst_mean, m.h_stage, b_mean);
     if (dst_rgba8) std::memcpy(dst_rgba8, m.h_stage + b_mean, b_rgba);
@@ -1625,7 +1835,29 @@ int Renderer::ResolvePeers(const uint8_t* handles, uint32_t n_ranks, uint32_t se
   return rc;
 }
 
+// Multi-device plumbing (rt_multi.cpp): an event on this renderer's stream after everything queued so far, and a wait of
+// this renderer's stream on another renderer's event.
+int Renderer::RecordDone(void** event_out) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (!m.ev_done) RT2_CUDA(cudaEventCreateWithFlags(&m.ev_done, cudaEventDisableTiming));
+  RT2_CUDA(cudaEventRecord(m.ev_done, m.stream));
+  *event_out = m.ev_done;
+  return RT2_OK;
+}
+int Renderer::WaitFor(void* event) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  RT2_CUDA(cudaStreamWaitEvent(m.stream, static_cast<cudaEvent_t>(event), 0));
+  return RT2_OK;
+}
+void* Renderer::AccumPtr() { return impl_->accum; }
+void* Renderer::AccumSqPtr() { return impl_->accum_sq; }
+
 int Renderer::AccumDevicePtr(void** ptr, size_t* n_floats) {
+  if (!state_ok_) return NoState();
+  int rc = Flush();  // whoever asks for the accumulator wants every requested frame in it (queued on the stream)
+  if (rc != RT2_OK) return rc;
   *ptr = impl_->accum;
   *n_floats = static_cast<size_t>(width_) * height_ * 4;
   return RT2_OK;
@@ -1637,7 +1869,7 @@ int Renderer::Intersect(const float* rays, size_t n, float tmin, float tmax, int
   Impl& m = *impl_;
   RT2_CUDA(cudaSetDevice(cfg_.device));
   if (n == 0) return RT2_OK;
-  if (n > 0x7FFFFFFFull) {
+  if (n > 0x3FFFFFFFull) {
     err_ = "too many rays";
     return RT2_ERR_INVALID_ARG;
   }
@@ -1650,59 +1882,111 @@ int Renderer::Intersect(const float* rays, size_t n, float tmin, float tmax, int
   float4* d_o = nullptr;
   float4* d_d = nullptr;
   uint4* d_trav = nullptr;
-  uint32_t* d_cursor = nullptr;
+  uint32_t* d_ctr = nullptr;  // [0] ray cursor, [1] entry count, [2] entry cursor
   rt2_hit* d_out = nullptr;
+  SplitIO io{};
   auto cleanup = [&]() {
-    if (d_o) cudaFree(d_o);
-    if (d_d) cudaFree(d_d);
-    if (d_trav) cudaFree(d_trav);
-    if (d_cursor) cudaFree(d_cursor);
-    if (d_out) cudaFree(d_out);
+    void* bufs[] = {d_o, d_d, d_trav, d_ctr, d_out, io.entries, io.entry_prim, io.inst_best};
+    for (void* b : bufs)
+      if (b) cudaFree(b);
   };
   cudaError_t e = cudaSuccess;
   if ((e = cudaMalloc(&d_o, n * sizeof(float4))) != cudaSuccess || (e = cudaMalloc(&d_d, n * sizeof(float4))) != cudaSuccess ||
-      (e = cudaMalloc(&d_trav, n * sizeof(uint4))) != cudaSuccess || (e = cudaMalloc(&d_cursor, sizeof(uint32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&d_trav, n * sizeof(uint4))) != cudaSuccess || (e = cudaMalloc(&d_ctr, 4 * sizeof(uint32_t))) != cudaSuccess ||
       (e = cudaMalloc(&d_out, n * sizeof(rt2_hit))) != cudaSuccess) {
     cleanup();
     err_ = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
     return RT2_ERR_CUDA;
   }
+  if (m.split_mode) {
+    // the same two-pass extend the renderer runs: entry queue sized for these rays
+    const size_t cap = n * m.ds.n_hoisted;
+    if ((e = cudaMalloc(&io.entries, cap * sizeof(uint2))) != cudaSuccess || (e = cudaMalloc(&io.entry_prim, cap * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&io.inst_best, n * sizeof(unsigned long long))) != cudaSuccess) {
+      cleanup();
+      err_ = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+      return RT2_ERR_CUDA;
+    }
+  }
   cudaMemcpyAsync(d_o, h_o.data(), n * sizeof(float4), cudaMemcpyHostToDevice, m.stream);
   cudaMemcpyAsync(d_d, h_d.data(), n * sizeof(float4), cudaMemcpyHostToDevice, m.stream);
-  cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t), m.stream);
+  cudaMemsetAsync(d_ctr, 0, 4 * sizeof(uint32_t), m.stream);
   const uint32_t n32 = static_cast<uint32_t>(n);
   const uint32_t grid = (n32 + kBlock - 1) / kBlock;
-  const uint32_t tgrid = grid < static_cast<uint32_t>(m.grid_extend) ? grid : static_cast<uint32_t>(m.grid_extend);
   const uint32_t seed_lo = static_cast<uint32_t>(cfg_.seed), seed_hi = static_cast<uint32_t>(cfg_.seed >> 32);
-  if (m.wide_mode) {
-    if (cfg_.flags & RT2_FLAG_FAST_MATH) {
-      k_traverse_wide<FastMath, false><<<tgrid, kBlock, 0, m.stream>>>(m.ds, m.wide, nullptr, n32, d_cursor, d_o, d_d, tmin, tmax, d_trav, nullptr, m.trav_max_steps);
-      k_finish_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
-    } else {
-      k_traverse_wide<ExactMath, false><<<tgrid, kBlock, 0, m.stream>>>(m.ds, m.wide, nullptr, n32, d_cursor, d_o, d_d, tmin, tmax, d_trav, nullptr, m.trav_max_steps);
-      k_finish_intersect<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
-    }
-  } else if (m.flat_mode) {
-    if (cfg_.flags & RT2_FLAG_FAST_MATH) {
-      k_traverse_flat<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, nullptr, n32, d_o, d_d, tmin, tmax, d_trav);
-      k_finish_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
-    } else {
-      k_traverse_flat<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, nullptr, n32, d_o, d_d, tmin, tmax, d_trav);
-      k_finish_intersect<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
-    }
-  } else if (cfg_.flags & RT2_FLAG_FAST_MATH) {
-    k_traverse_rays<FastMath><<<tgrid, kBlock, 0, m.stream>>>(m.ds, n32, d_cursor, d_o, d_d, tmin, tmax, d_trav);
-    k_finish_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
-  } else {
-    k_traverse_rays<ExactMath><<<tgrid, kBlock, 0, m.stream>>>(m.ds, n32, d_cursor, d_o, d_d, tmin, tmax, d_trav);
-    k_finish_intersect<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
-  }
-  launches_ += 2;
+  const bool exact = !(cfg_.flags & RT2_FLAG_FAST_MATH);
+  ExtendArgs ea{};
+  ea.n_ptr = nullptr;
+  ea.n_fixed = n32;
+  ea.cursor = d_ctr;
+  ea.entry_count = d_ctr + 1;
+  ea.entry_cursor = d_ctr + 2;
+  ea.ray_o = d_o;
+  ea.ray_d = d_d;
+  ea.tmin = tmin;
+  ea.tmax = tmax;
+  ea.trav = d_trav;
+  ea.io = io;
+  ea.grid = static_cast<int>(grid < static_cast<uint32_t>(m.grid_extend) ? grid : static_cast<uint32_t>(m.grid_extend));
+  ea.grid_flat = static_cast<int>(grid);
+  LaunchExtend(m, ea, exact, false, &launches_);
+  if (exact) k_finish_intersect<ExactMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, io, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
+  else k_finish_intersect<FastMath><<<grid, kBlock, 0, m.stream>>>(m.ds, d_o, d_d, d_trav, io, n32, tmin, skip_media, seed_lo, seed_hi, d_out);
+  launches_++;
   cudaMemcpyAsync(out, d_out, n * sizeof(rt2_hit), cudaMemcpyDeviceToHost, m.stream);
   e = cudaStreamSynchronize(m.stream);
   cleanup();
   if (e != cudaSuccess) {
     err_ = std::string("rt2_intersect kernels failed: ") + cudaGetErrorString(e);
+    return RT2_ERR_CUDA;
+  }
+  return CheckOverflow();
+}
+
+// Fixed-point parity hook for the device texture code: rgb[i] = textures[tex_idx].Value(u_i, v_i, p_i)
+// (Texture.cpp:7-22, PerlinNoiseGen.cpp:52-88) evaluated by the same texture_value() the shade kernels call.
+__global__ void __launch_bounds__(kBlock) k_texture_value(const DeviceScene S, uint32_t tex_idx, const float* __restrict__ pts,
+                                                          const float* __restrict__ uv, uint32_t n, float* __restrict__ rgb) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const F3 p = {pts[3 * i + 0], pts[3 * i + 1], pts[3 * i + 2]};
+  const F3 c = texture_value(S, tex_idx, p, uv ? uv[2 * i + 0] : 0.0f, uv ? uv[2 * i + 1] : 0.0f);
+  rgb[3 * i + 0] = c.x;
+  rgb[3 * i + 1] = c.y;
+  rgb[3 * i + 2] = c.z;
+}
+
+int Renderer::TextureValue(uint32_t tex_idx, const float* points, const float* uv, size_t n, float* rgb) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (n == 0) return RT2_OK;
+  if (tex_idx >= n_textures_ || n > 0x3FFFFFFFull) {
+    err_ = "rt2_texture_value: texture index out of range or too many points";
+    return RT2_ERR_INVALID_ARG;
+  }
+  float *d_p = nullptr, *d_uv = nullptr, *d_rgb = nullptr;
+  auto cleanup = [&]() {
+    if (d_p) cudaFree(d_p);
+    if (d_uv) cudaFree(d_uv);
+    if (d_rgb) cudaFree(d_rgb);
+  };
+  cudaError_t e = cudaSuccess;
+  if ((e = cudaMalloc(&d_p, n * 3 * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&d_rgb, n * 3 * sizeof(float))) != cudaSuccess ||
+      (uv && (e = cudaMalloc(&d_uv, n * 2 * sizeof(float))) != cudaSuccess)) {
+    cleanup();
+    err_ = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+    return RT2_ERR_CUDA;
+  }
+  cudaMemcpyAsync(d_p, points, n * 3 * sizeof(float), cudaMemcpyHostToDevice, m.stream);
+  if (uv) cudaMemcpyAsync(d_uv, uv, n * 2 * sizeof(float), cudaMemcpyHostToDevice, m.stream);
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  k_texture_value<<<(n32 + kBlock - 1) / kBlock, kBlock, 0, m.stream>>>(m.ds, tex_idx, d_p, d_uv, n32, d_rgb);
+  launches_++;
+  cudaMemcpyAsync(rgb, d_rgb, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, m.stream);
+  e = cudaStreamSynchronize(m.stream);
+  cleanup();
+  if (e != cudaSuccess) {
+    err_ = std::string("rt2_texture_value failed: ") + cudaGetErrorString(e);
     return RT2_ERR_CUDA;
   }
   return RT2_OK;
@@ -1716,7 +2000,7 @@ int Renderer::GetStats(rt2_stats* out) {
   RT2_CUDA(cudaMemcpy(t, m.totals, sizeof(t), cudaMemcpyDeviceToHost));
   out->rays = t[0];
   out->paths = t[1];
-  out->frames = frame_idx_;
+  out->frames = frame_idx_;  // Synchronize() above traced every pending frame
   out->launches = launches_;
   out->gpu_ms_total = gpu_ms_total_;
   out->gpu_ms_other = prof_ms_[0];
@@ -1729,6 +2013,10 @@ int Renderer::GetStats(rt2_stats* out) {
   out->sphere_tests = t[3];
   out->quad_tests = t[4];
   out->instance_visits = t[5];
+  out->stack_overflows = t[6];
+  out->pending_frames = pending_frames_;
+  out->n_gpus = 1;
+  out->instance_split = m.split_mode ? 1u : 0u;
   return RT2_OK;
 }
 
@@ -1777,6 +2065,68 @@ int MeasureFp32Peak(int device, double* tflops, std::string* err) {
   cudaFree(d);
   if (e != cudaSuccess) return fail("k_fma_peak", e);
   *tflops = best;
+  return RT2_OK;
+}
+
+// L2 read bandwidth, measured: every block streams a 24 MiB buffer (L2-resident on a B200: 126 MB of L2, but far beyond
+// the 148 x 256 KB of L1) with 16-byte loads, many times over; the first pass warms L2 and is not timed.
+__global__ void __launch_bounds__(256) k_l2_read(const float4* __restrict__ buf, uint32_t n_vec, int passes, float* __restrict__ out) {
+  float acc = 0.0f;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (int p = 0; p < passes; p++) {
+    // rotate the start so consecutive passes of a block do not re-read what its own L1 still holds
+    const uint32_t rot = static_cast<uint32_t>(p) * 0x9E3779B1u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+      const uint32_t j = (i + rot) % n_vec;
+      float4 v;
+      asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(buf + j));
+      acc += v.x + v.y + v.z + v.w;
+    }
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
+int MeasureL2Bandwidth(int device, double* gbs, std::string* err) {
+  auto fail = [&](const char* what, cudaError_t e) {
+    *err = std::string(what) + " failed: " + cudaGetErrorString(e);
+    return RT2_ERR_CUDA;
+  };
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  const size_t bytes = 24ull << 20;
+  const uint32_t n_vec = static_cast<uint32_t>(bytes / sizeof(float4));
+  float4* d = nullptr;
+  float* out = nullptr;
+  if ((e = cudaMalloc(&d, bytes)) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMalloc(&out, sizeof(float))) != cudaSuccess) {
+    cudaFree(d);
+    return fail("cudaMalloc", e);
+  }
+  cudaMemset(d, 0, bytes);
+  const int blocks = prop.multiProcessorCount * 8, passes = 16;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = 0;
+  k_l2_read<<<blocks, 256>>>(d, n_vec, 1, out);  // warm L2
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(a);
+    k_l2_read<<<blocks, 256>>>(d, n_vec, passes, out);
+    cudaEventRecord(b);
+    if ((e = cudaEventSynchronize(b)) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double g = static_cast<double>(bytes) * passes / (ms * 1e-3) * 1e-9;
+    if (ms > 0 && g > best) best = g;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  cudaFree(out);
+  if (e != cudaSuccess) return fail("k_l2_read", e);
+  *gbs = best;
   return RT2_OK;
 }
 

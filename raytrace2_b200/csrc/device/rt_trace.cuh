@@ -28,7 +28,9 @@ struct DeviceScene {
   uint32_t n_images;
   const uint32_t* __restrict__ prim_refs;
   const float4* __restrict__ nodes;  // 4 x float4 per node pair
-  uint32_t tlas_root;
+  uint32_t tlas_root;        // world TLAS with the instances as singleton leaves (kTravInline)
+  uint32_t tlas_world_root;  // world TLAS over surfaces only (kTravWorld: the instances are hoisted out of the tree)
+  uint32_t n_hoisted;        // > 0: instance split — all n_instances (<= kMaxHoistedInstances) are hoisted
   uint32_t n_media;
   uint32_t n_instances;
   float min_inv_scale;
@@ -36,7 +38,7 @@ struct DeviceScene {
   // flat mode (tiny scenes, traverse_flat): every leaf primitive listed by space
   const uint32_t* __restrict__ flat_refs;     // world primitives, then the primitives of instance 0, 1, ...
   const uint32_t* __restrict__ flat_offsets;  // n_instances + 2 offsets into flat_refs
-  const float4* __restrict__ flat_inst_bounds;  // 2 x float4 per instance: world-space box
+  const float4* __restrict__ inst_bounds;   // 2 x float4 per instance: conservative world-space box (flat mode, instance split)
   float sort_lo[3];     // ray-sort grid (rt_sort.cuh): robust scene bounds, 32 cells per axis
   float sort_scale[3];
 };
@@ -53,7 +55,6 @@ __host__ __device__ inline uint32_t make_leaf_entry(uint32_t first, uint32_t cou
   return count == 1u ? (kLeafFlag | kLeafDirect | ref_if_single) : (kLeafFlag | ((count - 1u) << 26) | first);
 }
 constexpr int kStackSize = 64;
-#define RT2_STACK_GUARD if (sp < kStackSize)
 
 struct RaySpace {
   F3 o, d;
@@ -190,6 +191,20 @@ struct Closest {
   int32_t instance;   // flattened instance index, -1 = world space
 };
 
+// Exact ties.  BVHNode::Hit and HittableList::Hit visit the leaves in a fixed order with a shrinking tmax (BVH.cpp:50-55,
+// HittableList.cpp:8-22); Quad::Hit accepts t == tmax (closed interval, Quad.cpp:27), Sphere::Hit does not (Sphere.cpp:21).
+// So among coincident faces (adjacent boxes of the book-2 grid, a box standing on the floor) the quad visited LAST by the
+// reference wins, and a quad always beats a sphere at the same t.  Our traversal order is different, so the order is
+// carried as a rank per quad (rt2_quad.pad1, host/scene_host.cpp: position in the reference's leaf order) and consulted
+// only when t ties exactly.
+__device__ __forceinline__ bool quad_wins_tie(const DeviceScene& S, float t, uint32_t ref, const Closest& best) {
+  if (t < best.t) return true;
+  if (best.prim == RT2_PRIM_NONE || RT2_PRIM_TYPE(best.prim) != RT2_PRIM_QUAD) return true;
+  const uint32_t rank_new = __float_as_uint(__ldg(S.quads + 5 * RT2_PRIM_INDEX(ref) + 3).w);
+  const uint32_t rank_old = __float_as_uint(__ldg(S.quads + 5 * RT2_PRIM_INDEX(best.prim) + 3).w);
+  return rank_new > rank_old;
+}
+
 // HittableList::Hit over a short list of surface primitives (HittableList.cpp:8-22): shrinking tmax, later closed-
 // interval ties win.  Used for medium boundaries.
 template <class M>
@@ -218,28 +233,80 @@ __device__ __forceinline__ bool list_hit(const DeviceScene& S, uint32_t first, u
 // Per-lane traversal counters (profiling build of k_traverse): algorithmic work actually done by ACTIVE lanes.
 struct TravCounters {
   uint32_t box_pairs{0}, spheres{0}, quads{0}, instances{0};
+  uint32_t overflow{0};  // a push found the traversal stack full (always tracked)
 };
 
 // Surface traversal of a whole ray queue by persistent warps (one lane = one ray at a time).
 //
-// Two-level BVH: world TLAS whose (singleton) instance leaves switch the lane to the instance's model space and BLAS;
-// a sentinel on the stack switches back.  Box tests only cull and are conservative (see cull_scale), so the result is
-// the exact arg-min over leaves of the raw reported t.
+// Two-level BVH: world TLAS + one BLAS per instance.  Box tests only cull and are conservative (see cull_scale), so the
+// result is the exact arg-min over leaves of the raw reported t.  Three modes share the walk:
+//
+//   kTravInline  the TLAS holds the instances as singleton leaves; a lane that meets one switches to the instance's model
+//                space and BLAS, a sentinel on the stack switches it back (scenes with many instances).
+//   kTravWorld   "instance split", pass 1: the TLAS holds surfaces only and is culled with the exact bound.  When a ray is
+//                finished, its segment [0, best.t * cull_scale] is tested against the world boxes of the (few, hoisted)
+//                instances — at the warp's convergence point, so all finished lanes do it together — and every touched
+//                instance becomes one entry {ray, instance} of the bounce's entry queue.
+//   kTravInst    pass 2: one lane = one entry.  The exact-arithmetic world-to-model transforms (Transform.cpp:13-20) run with
+//                the whole warp converged, the walk starts at the BLAS root with tmax = the ray's closest world surface,
+//                and a hit is merged into the ray's slot by a 64-bit atomicMin on (ordered t, entry index).
+//                Consumers read the merged record through load_closest().
 //
 // SIMT shape ("while-while" with dynamic fetch, after Aila & Laine 2009): the warp alternates between
 //   phase 1  every lane descends interior nodes until it holds a leaf (or its ray is finished),
 //   phase 2  every lane that holds a leaf intersects its primitives,
+//   publish  every lane whose ray is finished writes its result,
 // reconverging with __syncwarp() between the phases, so the expensive exact-arithmetic primitive tests run with many
-// lanes instead of whichever lanes happen to reach a leaf in the same iteration.  Lanes whose ray is finished write
-// the result and idle; when fewer than kFetchThreshold lanes are busy the warp pulls new rays from the queue with one
-// atomic.  `order` (optional) is the permutation in which the queue is consumed.  Results go to
-// trav_out[ray] = {t bits, prim ref, instance, 0}.
-template <class M, bool kCount, int kFetchThreshold, int kVar = 0>
+// lanes instead of whichever lanes happen to reach a leaf in the same iteration.  When fewer than `fetch_threshold` lanes
+// are busy the warp pulls new work from the queue with one atomic.  `order` (optional) is the permutation in which the
+// queue is consumed.  Results go to trav_out[ray] = {t bits, prim ref, instance, has-entries flag}.
+enum { kTravInline = 0, kTravWorld = 1, kTravInst = 2 };
+constexpr uint32_t kTravDone = 0xFFFFFFFFu;  // `cur` of a lane whose ray is finished (carries kLeafFlag: phase 1 skips it)
+constexpr uint32_t kMaxHoistedInstances = 4;
+
+// Plumbing of the instance split (device buffers owned by the renderer).
+struct SplitIO {
+  uint2* entries;                  // {ray index, instance index}
+  uint32_t* entry_prim;            // per entry: winning primitive inside the instance (valid when it won)
+  unsigned long long* inst_best;   // per ray: ordered(t) << 32 | entry index, minimum over the ray's entries
+  uint32_t* entry_count;           // entries of this bounce
+};
+
+// Monotone map float -> uint32 (also for negative t of caller-supplied intervals) and back.
+__device__ __forceinline__ uint32_t ordered_bits(float t) {
+  const uint32_t b = __float_as_uint(t);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+
+// The closest SURFACE of ray i after the extend kernels: the world pass's record, replaced by the best instance entry of
+// the ray when that one is closer (strictly: an exact tie keeps the world-space primitive).
+__device__ __forceinline__ uint4 load_closest(const uint4* __restrict__ trav, const SplitIO& io, uint32_t i) {
+  uint4 tr = trav[i];
+  if (tr.w != 0u) {
+    const unsigned long long b = io.inst_best[i];
+    if (b != ~0ull) {
+      const float t = from_ordered_bits(static_cast<uint32_t>(b >> 32));
+      if (t < __uint_as_float(tr.x)) {
+        const uint32_t e = static_cast<uint32_t>(b);
+        tr.x = __float_as_uint(t);
+        tr.y = io.entry_prim[e];
+        tr.z = io.entries[e].y;
+      }
+    }
+    tr.w = 0u;
+  }
+  return tr;
+}
+
+template <class M, bool kCount, int kMode>
 __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n, const float4* __restrict__ ray_o,
                                                const float4* __restrict__ ray_d, float tmin, float tmax,
                                                uint32_t* __restrict__ next_ray, const uint32_t* __restrict__ order,
-                                               uint4* __restrict__ trav_out, TravCounters& cnt, int max_steps = 1 << 30,
-                                               int fetch_threshold = kFetchThreshold) {
+                                               uint4* __restrict__ trav_out, const SplitIO& io, TravCounters& cnt,
+                                               int max_steps, int fetch_threshold) {
   const unsigned kFull = 0xFFFFFFFFu;
   const unsigned lane = threadIdx.x & 31u;
   uint32_t stack[kStackSize];
@@ -247,11 +314,12 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
   bool active = false;
   bool exhausted = false;
   uint32_t ray_idx = 0;
+  uint32_t entry_idx = 0;  // kTravInst
   uint32_t cur = 0;
   F3 o = {0, 0, 0}, d = {0, 0, 1};
   float time = 0.0f, a = 1.0f;
   F3 inv = {0, 0, 0}, oid = {0, 0, 0};
-  float cull_scale = 1.0f, cur_cull = 1.0f;
+  float cull_scale = 1.0f, cur_cull = 1.0f;  // kTravInline
   int32_t cur_inst = -1;
   Closest best{tmax, RT2_PRIM_NONE, -1};
 
@@ -262,28 +330,36 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
     inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
     oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
   };
-  // Pops the next entry; on an empty stack the ray is finished: publish the result and free the lane.
+  // The builders bound the depth of every tree; should a tree ever be deeper than the stack, the dropped sub-tree is
+  // counted (rt2_stats.stack_overflows) and the read-out calls fail instead of returning a silently wrong image.
+  auto push = [&](uint32_t v) {
+    if (sp < kStackSize) stack[sp++] = v;
+    else cnt.overflow = 1u;
+  };
+  // Pops the next entry; on an empty stack the ray is finished (published at the end of the round).
   auto pop = [&]() {
-    while (true) {
-      if (sp == 0) {
-        const uint4 res = make_uint4(__float_as_uint(best.t), best.prim, static_cast<uint32_t>(best.instance), 0u);
-        if (kVar & 1) __stcs(trav_out + ray_idx, res);  // streaming: the queues must not evict the scene from L1
-        else trav_out[ray_idx] = res;
-        active = false;
-        return;
+    if (kMode == kTravInline) {
+      while (true) {
+        if (sp == 0) {
+          cur = kTravDone;
+          return;
+        }
+        cur = stack[--sp];
+        if (cur != kStackSentinel) return;
+        // leave the instance: back to the world-space ray (re-read instead of holding it in registers)
+        const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
+        set_space(make_f3(wo), make_f3(wd));
+        cur_inst = -1;
+        cur_cull = cull_scale;
       }
-      cur = stack[--sp];
-      if (cur != kStackSentinel) return;
-      // leave the instance: back to the world-space ray (re-read instead of holding it in registers)
-      const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
-      set_space(make_f3(wo), make_f3(wd));
-      cur_inst = -1;
-      cur_cull = cull_scale;
+    } else {
+      cur = kTravDone;
+      if (sp > 0) cur = stack[--sp];
     }
   };
 
   while (true) {
-    // ---- fetch: idle lanes take the next rays of the queue (one atomic per warp) ----
+    // ---- fetch: idle lanes take the next items of the queue (one atomic per warp) ----
     const unsigned idle = __ballot_sync(kFull, !active);
     if (idle) {
       if (!exhausted) {
@@ -294,22 +370,38 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         if (!active) {
           const uint32_t pos = base + __popc(idle & ((1u << lane) - 1u));
           if (pos < n) {
-            const uint32_t idx = order ? order[pos] : pos;  // rt_sort.cuh: coherence order of the queue
-            ray_idx = idx;
-            const float4 wo = (kVar & 1) ? __ldcs(ray_o + idx) : ray_o[idx];
-            const float4 wd = (kVar & 1) ? __ldcs(ray_d + idx) : ray_d[idx];
-            time = wo.w;
-            set_space(make_f3(wo), make_f3(wd));
-            // An instanced leaf reports t in model units (= world t * |M^-1 d|): a world-space box at parameter t_w can
-            // hold an instanced hit with raw t as small as t_w * sigma_min * |d|, so scale the TLAS culling bound.
-            cull_scale = (S.n_instances > 0) ? fmaxf(1.0f, 1.0f / (S.min_inv_scale * sqrtf(a))) : 1.0f;
-            cur_cull = cull_scale;
-            cur_inst = -1;
-            best.t = tmax;
+            if (kMode == kTravInst) {
+              // one entry: the ray in the instance's model space, bounded by its closest world-space surface
+              entry_idx = pos;
+              const uint2 ent = io.entries[pos];
+              ray_idx = ent.x;
+              const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
+              time = wo.w;
+              const uint4 in = __ldg(S.instances + ent.y);
+              const RaySpace ms = to_chain_space<M>(S, in.x, in.y, RaySpace{make_f3(wo), make_f3(wd)});
+              set_space(ms.o, ms.d);
+              cur_inst = static_cast<int32_t>(ent.y);
+              best.t = __uint_as_float(trav_out[ray_idx].x);
+              cur = in.z;
+            } else {
+              const uint32_t idx = order ? order[pos] : pos;  // rt_sort.cuh: coherence order of the queue
+              ray_idx = idx;
+              const float4 wo = ray_o[idx], wd = ray_d[idx];
+              time = wo.w;
+              set_space(make_f3(wo), make_f3(wd));
+              if (kMode == kTravInline) {
+                // An instanced leaf reports t in model units (= world t * |M^-1 d|): a world-space box at parameter t_w can
+                // hold an instanced hit with raw t as small as t_w * sigma_min * |d|, so scale the TLAS culling bound.
+                cull_scale = (S.n_instances > 0) ? fmaxf(1.0f, 1.0f / (S.min_inv_scale * sqrtf(a))) : 1.0f;
+                cur_cull = cull_scale;
+                cur_inst = -1;
+              }
+              best.t = tmax;
+              cur = (kMode == kTravWorld) ? S.tlas_world_root : S.tlas_root;
+            }
             best.prim = RT2_PRIM_NONE;
             best.instance = -1;
             sp = 0;
-            cur = S.tlas_root;
             active = true;
           }
         }
@@ -327,7 +419,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         if (kCount) cnt.box_pairs++;
         // conservative culling: near is shrunk by 1e-6 relative before it is compared with far and with the (scaled)
         // closest hit so far; an empty slot has NaN bounds -> far is NaN -> never entered
-        const float bound = best.t * cur_cull;
+        const float bound = (kMode == kTravInline) ? best.t * cur_cull : best.t;
         float t0x = fmaf(a0.x, inv.x, oid.x), t1x = fmaf(a1.x, inv.x, oid.x);
         float t0y = fmaf(a0.y, inv.y, oid.y), t1y = fmaf(a1.y, inv.y, oid.y);
         float t0z = fmaf(a0.z, inv.z, oid.z), t1z = fmaf(a1.z, inv.z, oid.z);
@@ -348,7 +440,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         if (h0 && h1) {
           const bool swap = near1 < near0;
           cur = swap ? e1 : e0;
-          RT2_STACK_GUARD stack[sp++] = swap ? e0 : e1;  // the host builder bounds the depth; never write past the stack
+          push(swap ? e0 : e1);
         } else if (h0) {
           cur = e0;
         } else if (h1) {
@@ -359,7 +451,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
       }
       __syncwarp();
       // phase 2: leaves
-      if (active && (cur & kLeafFlag)) {
+      if (active && (cur & kLeafFlag) && cur != kTravDone) {
         const bool direct = (cur & kLeafDirect) != 0u;
         const uint32_t first = cur & 0x03FFFFFFu;
         const uint32_t count = direct ? 1u : (((cur >> 26) & 0xFu) + 1u);
@@ -378,13 +470,17 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
           } else if (type == RT2_PRIM_QUAD) {
             if (kCount) cnt.quads++;
             float t;
-            if (quad_hit<M>(S.quads + 5 * idx, o, d, tmin, best.t, t)) {
+            if (quad_hit<M>(S.quads + 5 * idx, o, d, tmin, best.t, t) && quad_wins_tie(S, t, ref, best)) {
               best.t = t;
               best.prim = ref;
               best.instance = cur_inst;
             }
-          } else {
+          } else if (kMode == kTravInline) {
             // instance leaf (always a singleton leaf of the TLAS, host/bvh_build.cpp): enter its BLAS in model space
+            if (sp >= kStackSize) {  // no room for the way back: skip the instance and report it
+              cnt.overflow = 1u;
+              continue;
+            }
             if (kCount) cnt.instances++;
             const uint4 in = __ldg(S.instances + idx);
             const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
@@ -392,7 +488,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
             set_space(ms.o, ms.d);
             cur_inst = static_cast<int32_t>(idx);
             cur_cull = 1.0f;
-            RT2_STACK_GUARD stack[sp++] = kStackSentinel;
+            stack[sp++] = kStackSentinel;
             cur = in.z;
             entered = true;
             break;
@@ -401,6 +497,55 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         if (!entered) pop();
       }
       __syncwarp();
+      // publish: finished rays, with the whole warp converged
+      const bool fin = active && cur == kTravDone;
+      if (kMode == kTravWorld) {
+        bool has_entry = false;
+        if (S.n_hoisted > 0u && __ballot_sync(kFull, fin) != 0u) {
+          // which hoisted instances can still beat the closest world-space surface?  An instanced leaf reports t in model
+          // units (= world t * |M^-1 d|), so the segment tested against the world box ends at best.t * cull_scale.
+          const float bound = best.t * fmaxf(1.0f, 1.0f / (S.min_inv_scale * sqrtf(a)));
+          for (uint32_t j = 0; j < S.n_hoisted; j++) {
+            const float4 bmn = __ldg(S.inst_bounds + 2 * j), bmx = __ldg(S.inst_bounds + 2 * j + 1);
+            const float t0x = fmaf(bmn.x, inv.x, oid.x), t1x = fmaf(bmx.x, inv.x, oid.x);
+            const float t0y = fmaf(bmn.y, inv.y, oid.y), t1y = fmaf(bmx.y, inv.y, oid.y);
+            const float t0z = fmaf(bmn.z, inv.z, oid.z), t1z = fmaf(bmx.z, inv.z, oid.z);
+            const float nr = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f)) * 0.999999f;
+            const float fr = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+            const bool touch = fin && (nr <= fr) && (nr <= bound);
+            const unsigned tm = __ballot_sync(kFull, touch);
+            if (tm) {
+              const int leader = __ffs(tm) - 1;
+              uint32_t base = 0;
+              if (static_cast<int>(lane) == leader) base = atomicAdd(io.entry_count, __popc(tm));
+              base = __shfl_sync(kFull, base, leader);
+              if (touch) {
+                io.entries[base + __popc(tm & ((1u << lane) - 1u))] = make_uint2(ray_idx, j);
+                has_entry = true;
+                if (kCount) cnt.instances++;
+              }
+            }
+          }
+        }
+        if (fin) {
+          trav_out[ray_idx] = make_uint4(__float_as_uint(best.t), best.prim, 0xFFFFFFFFu, has_entry ? 1u : 0u);
+          if (has_entry) io.inst_best[ray_idx] = ~0ull;
+          active = false;
+        }
+      } else if (kMode == kTravInst) {
+        if (fin) {
+          if (best.prim != RT2_PRIM_NONE) {
+            atomicMin(io.inst_best + ray_idx, (static_cast<unsigned long long>(ordered_bits(best.t)) << 32) | entry_idx);
+            io.entry_prim[entry_idx] = best.prim;
+          }
+          active = false;
+        }
+      } else {
+        if (fin) {
+          trav_out[ray_idx] = make_uint4(__float_as_uint(best.t), best.prim, static_cast<uint32_t>(best.instance), 0u);
+          active = false;
+        }
+      }
       const unsigned busy = __ballot_sync(kFull, active);
       if (busy == 0u) break;
       if (!exhausted && __popc(busy) < fetch_threshold) break;
@@ -429,7 +574,7 @@ __device__ __forceinline__ void flat_test_range(const DeviceScene& S, uint32_t f
     } else {
       h = quad_hit<M, true>(S.quads + 5 * idx, o, d, tmin, best.t, t);
     }
-    if (h && lane_on) {
+    if (h && lane_on && (RT2_PRIM_TYPE(ref) == RT2_PRIM_SPHERE || quad_wins_tie(S, t, ref, best))) {
       best.t = t;
       best.prim = ref;
       best.instance = inst;
@@ -444,7 +589,7 @@ __device__ __forceinline__ Closest traverse_flat(const DeviceScene& S, F3 wo, F3
   const float ix = safe_rcp(wd.x), iy = safe_rcp(wd.y), iz = safe_rcp(wd.z);
   for (uint32_t j = 0; j < S.n_instances; j++) {
     // conservative world-box test of the whole ray (no bound by best.t: an instanced leaf reports t in model units)
-    const float4 bmn = __ldg(S.flat_inst_bounds + 2 * j), bmx = __ldg(S.flat_inst_bounds + 2 * j + 1);
+    const float4 bmn = __ldg(S.inst_bounds + 2 * j), bmx = __ldg(S.inst_bounds + 2 * j + 1);
     const float ax = (bmn.x - wo.x) * ix, bx = (bmx.x - wo.x) * ix;
     const float ay = (bmn.y - wo.y) * iy, by = (bmx.y - wo.y) * iy;
     const float az = (bmn.z - wo.z) * iz, bz = (bmx.z - wo.z) * iz;

@@ -178,9 +178,18 @@ __device__ __forceinline__ void traverse_queue_wide(const DeviceScene& S, const 
         } else {
           cur = ent[0];
           // push the others farthest first, so that the nearest is popped first
-          if (nearv[3] != kFltMax && sp < kWideStack) stack[sp++] = ent[3];
-          if (nearv[2] != kFltMax && sp < kWideStack) stack[sp++] = ent[2];
-          if (nearv[1] != kFltMax && sp < kWideStack) stack[sp++] = ent[1];
+          if (nearv[3] != kFltMax) {
+            if (sp < kWideStack) stack[sp++] = ent[3];
+            else cnt.overflow = 1u;
+          }
+          if (nearv[2] != kFltMax) {
+            if (sp < kWideStack) stack[sp++] = ent[2];
+            else cnt.overflow = 1u;
+          }
+          if (nearv[1] != kFltMax) {
+            if (sp < kWideStack) stack[sp++] = ent[1];
+            else cnt.overflow = 1u;
+          }
         }
       }
       __syncwarp();

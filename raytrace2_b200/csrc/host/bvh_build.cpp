@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "scene_host.hpp"
+#include "tuning.hpp"
 
 namespace rt2 {
 namespace {
@@ -18,20 +19,16 @@ constexpr int kBins = 16;
 // Leaf policy: a range of <= MaxLeaf() primitives becomes a leaf when the SAH says splitting does not pay (default 1: on
 // the GPU the leaf phase of the while-while walk runs at ~6 of 32 lanes, so one-primitive leaves measured 2-8 % faster
 // than leaves of up to 4, profiles/r01_notes.md; longer leaves only appear behind the depth guard), with one
-// node-pair visit costed as TravCost() primitive tests.  Overridable for tuning runs (RT2_BVH_MAX_LEAF, RT2_BVH_TRAV_COST).
+// node-pair visit costed as TravCost() primitive tests.  Overridable only in EXPERIMENTS builds (host/tuning.hpp).
 uint32_t MaxLeaf() {
   static const uint32_t v = [] {
-    const char* e = std::getenv("RT2_BVH_MAX_LEAF");
-    int x = e ? std::atoi(e) : 1;
+    const long x = TuneInt("RT2_BVH_MAX_LEAF", 1);
     return static_cast<uint32_t>(x < 1 ? 1 : (x > 16 ? 16 : x));
   }();
   return v;
 }
 float TravCost() {
-  static const float v = [] {
-    const char* e = std::getenv("RT2_BVH_TRAV_COST");
-    return e ? static_cast<float>(std::atof(e)) : 2.5f;
-  }();
+  static const float v = static_cast<float>(TuneFloat("RT2_BVH_TRAV_COST", 2.5));
   return v;
 }
 constexpr int kMaxDepth = 40;  // beyond this: median splits (<= 24 more levels for 16M prims; the device stack holds 64)

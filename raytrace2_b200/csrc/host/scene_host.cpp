@@ -502,6 +502,10 @@ struct Flattener {
       world.mx[k] += pad;
     }
     tlas.push_back(MakeBuildPrim(world, (RT2_PRIM_INSTANCE << 28) | static_cast<uint32_t>(sc->instances.size() - 1)));
+    for (int k = 0; k < 3; k++) sc->inst_bounds.push_back(world.mn[k]);
+    sc->inst_bounds.push_back(0.f);
+    for (int k = 0; k < 3; k++) sc->inst_bounds.push_back(world.mx[k]);
+    sc->inst_bounds.push_back(0.f);
   }
 
   std::vector<double> level_sigma_;
@@ -512,10 +516,29 @@ int Compile(Builder& b, std::string* err) {
   sc->n_top_level = static_cast<uint32_t>(b.top.size());
   // Q2 flags from the reference-order BVH
   sc->span1_flags.assign(b.top.size(), 0);
+  std::vector<ReplayItem> ref_order(b.top.size());  // the top-level objects in the reference BVH's leaf order
   if (!b.top.empty()) {
-    std::vector<ReplayItem> objs(b.top.size());
-    for (size_t i = 0; i < b.top.size(); i++) objs[i] = ReplayItem{NodeRefBox(b.top[i], b.prims), static_cast<uint32_t>(i)};
-    ReplayReferenceBVH(objs, 0, objs.size(), sc->span1_flags);
+    for (size_t i = 0; i < b.top.size(); i++) ref_order[i] = ReplayItem{NodeRefBox(b.top[i], b.prims), static_cast<uint32_t>(i)};
+    ReplayReferenceBVH(ref_order, 0, ref_order.size(), sc->span1_flags);
+  }
+  // Tie ranks (device quad_wins_tie): position of every quad in the order in which the reference's BVH visits the leaves —
+  // its top-level objects left to right (BVH.cpp:50-55: always left, then right), each object's own list in list order
+  // (own primitive, then children; HittableList.cpp:8-22).  Stored as integer bits in rt2_quad.pad1.
+  {
+    uint32_t next_rank = 1;
+    std::vector<uint8_t> ranked(sc->quads.size(), 0);
+    auto rank_node = [&](const Node& n, auto&& self) -> void {
+      if (n.primitive >= 0) {
+        for (uint32_t r : b.prims[static_cast<size_t>(n.primitive)].refs) {
+          if (RT2_PRIM_TYPE(r) != RT2_PRIM_QUAD || ranked[RT2_PRIM_INDEX(r)]) continue;
+          ranked[RT2_PRIM_INDEX(r)] = 1;
+          const uint32_t v = next_rank++;
+          std::memcpy(&sc->quads[RT2_PRIM_INDEX(r)].pad1, &v, sizeof(v));
+        }
+      }
+      for (const Node& c : n.children) self(c, self);
+    };
+    for (const ReplayItem& it : ref_order) rank_node(b.top[it.idx], rank_node);
   }
   Flattener fl{sc, &b.prims, {}, {}};
   sc->min_inv_scale = 1.0f;
@@ -523,6 +546,15 @@ int Compile(Builder& b, std::string* err) {
   sc->tlas_root = BuildBVH(fl.tlas, sc);
   sc->tree_prims.resize(sc->instances.size() + 1);
   sc->tree_prims[0] = fl.tlas;
+  // instance split: a second world tree without the instance leaves (RT2_MAX_HOISTED_INSTANCES)
+  sc->has_world_tlas = false;
+  if (!sc->instances.empty() && sc->instances.size() <= RT2_MAX_HOISTED_INSTANCES) {
+    std::vector<BuildPrim> surfaces;
+    for (const BuildPrim& p : fl.tlas)
+      if (RT2_PRIM_TYPE(p.ref) != RT2_PRIM_INSTANCE) surfaces.push_back(p);
+    sc->tlas_world_root = BuildBVH(surfaces, sc);
+    sc->has_world_tlas = true;
+  }
   sc->UpdateCamera();
   (void)err;
   return RT2_OK;
@@ -939,6 +971,9 @@ void HostScene::FillDesc(rt2_scene_desc* d) const {
   d->n_image_texels = static_cast<uint32_t>(image_texels.size() / 4);
   d->images = images.data();
   d->image_texels = image_texels.data();
+  d->has_world_tlas = has_world_tlas ? 1u : 0u;
+  d->tlas_world_root = tlas_world_root;
+  d->inst_bounds = inst_bounds.data();
 }
 
 int LoadSceneString(const std::string& text, const std::string& data_dir, uint64_t perlin_seed, HostScene* out,

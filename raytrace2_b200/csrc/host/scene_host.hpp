@@ -43,6 +43,11 @@ struct HostScene {
   std::vector<uint32_t> prim_refs;
   std::vector<rt2_bvh_node> nodes;  // 2 per pair
   uint32_t tlas_root{0};
+  // Instance split (device/rt_trace.cuh kTravWorld): scenes with 1..RT2_MAX_HOISTED_INSTANCES instances also get a world TLAS
+  // over the surfaces only; the instances are then tested by their world boxes (inst_bounds) after the world walk.
+  uint32_t tlas_world_root{0};
+  bool has_world_tlas{false};
+  std::vector<float> inst_bounds;  // 8 floats per instance: conservative world-space AABB (min xyz 0, max xyz 0)
   uint32_t n_top_level{0};
   std::vector<uint8_t> span1_flags;  // per top-level node (Q2)
   // Leaf records of every tree, kept for the device-side LBVH build (RT2_FLAG_GPU_LBVH): [0] = world TLAS,

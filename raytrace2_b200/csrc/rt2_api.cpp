@@ -11,7 +11,7 @@
 #include <sys/stat.h>
 
 #include "../../include/rt2.h"
-#include "device/rt_render.hpp"
+#include "device/rt_multi.hpp"
 #include "host/image_out.hpp"
 #include "host/scene_host.hpp"
 
@@ -19,7 +19,7 @@ struct rt2_scene {
   rt2::HostScene host;
 };
 struct rt2_renderer {
-  rt2::Renderer impl;
+  rt2::MultiRenderer impl;  // one wavefront renderer per GPU behind the handle (device/rt_multi.hpp)
 };
 
 namespace {
@@ -39,6 +39,12 @@ int rt2_measure_fp32_peak(int32_t device, double* tflops) {
   if (!tflops) return Fail(RT2_ERR_INVALID_ARG, "null argument");
   std::string err;
   int rc = rt2::MeasureFp32Peak(device, tflops, &err);
+  return rc == RT2_OK ? RT2_OK : Fail(rc, err);
+}
+int rt2_measure_l2_bandwidth(int32_t device, double* gbs) {
+  if (!gbs) return Fail(RT2_ERR_INVALID_ARG, "null argument");
+  std::string err;
+  int rc = rt2::MeasureL2Bandwidth(device, gbs, &err);
   return rc == RT2_OK ? RT2_OK : Fail(rc, err);
 }
 
@@ -182,6 +188,7 @@ int rt2_upload_scene(rt2_renderer* r, const rt2_scene* scene) {
 int rt2_resize(rt2_renderer* r, int32_t width, int32_t height) { RT2_FORWARD(r->impl.Resize(width, height)) }
 int rt2_reset(rt2_renderer* r) { RT2_FORWARD(r->impl.Reset()) }
 int rt2_update(rt2_renderer* r, uint32_t n_frames) { RT2_FORWARD(r->impl.Update(n_frames)) }
+int rt2_flush(rt2_renderer* r) { RT2_FORWARD(r->impl.Flush()) }
 int rt2_synchronize(rt2_renderer* r) { RT2_FORWARD(r->impl.Synchronize()) }
 int rt2_frame_idx(const rt2_renderer* r, uint64_t* out) {
   if (!r || !out) return Fail(RT2_ERR_INVALID_ARG, "null argument");
@@ -206,31 +213,54 @@ int rt2_read_accum(rt2_renderer* r, float* sum, float* sumsq) { RT2_FORWARD(r->i
 int rt2_write_accum(rt2_renderer* r, const float* sum, const float* sumsq, uint64_t frames) {
   RT2_FORWARD(r->impl.WriteAccum(sum, sumsq, frames))
 }
+// The next four calls are the plumbing of the one-process-per-GPU harness (external NCCL reduce, CUDA IPC read-out); a
+// multi-GPU handle reduces over peer memory by itself and rejects them.
+#define RT2_SINGLE(what)                                               \
+  if (!r) return Fail(RT2_ERR_INVALID_ARG, "null renderer");           \
+  rt2::Renderer* one = r->impl.Single(what);                           \
+  if (!one) return Fail(RT2_ERR_UNSUPPORTED, r->impl.Error());
+#define RT2_SINGLE_RC(expr)                             \
+  {                                                     \
+    int rc__ = (expr);                                  \
+    if (rc__ != RT2_OK) return Fail(rc__, one->Error()); \
+    return RT2_OK;                                      \
+  }
 int rt2_accum_ipc_handle(rt2_renderer* r, uint8_t* handle) {
   if (!handle) return Fail(RT2_ERR_INVALID_ARG, "null argument");
-  RT2_FORWARD(r->impl.AccumIpcHandle(handle))
+  RT2_SINGLE("rt2_accum_ipc_handle")
+  RT2_SINGLE_RC(one->AccumIpcHandle(handle))
 }
 int rt2_resolve_peers(rt2_renderer* r, const uint8_t* handles, uint32_t n_ranks, uint32_t self_rank, uint64_t total_frames, float* dst_mean_rgb,
                       uint8_t* dst_rgba8) {
-  RT2_FORWARD(r->impl.ResolvePeers(handles, n_ranks, self_rank, total_frames, dst_mean_rgb, dst_rgba8))
+  RT2_SINGLE("rt2_resolve_peers")
+  RT2_SINGLE_RC(one->ResolvePeers(handles, n_ranks, self_rank, total_frames, dst_mean_rgb, dst_rgba8))
 }
 int rt2_accum_device_ptr(rt2_renderer* r, void** ptr, size_t* n_floats) {
   if (!ptr || !n_floats) return Fail(RT2_ERR_INVALID_ARG, "null argument");
-  RT2_FORWARD(r->impl.AccumDevicePtr(ptr, n_floats))
+  RT2_SINGLE("rt2_accum_device_ptr")
+  RT2_SINGLE_RC(one->AccumDevicePtr(ptr, n_floats))
 }
-int rt2_set_frame_idx(rt2_renderer* r, uint64_t frames) {
-  if (!r) return Fail(RT2_ERR_INVALID_ARG, "null renderer");
-  r->impl.SetFrameIdx(frames);
-  return RT2_OK;
-}
+int rt2_set_frame_idx(rt2_renderer* r, uint64_t frames) { RT2_FORWARD(r->impl.SetFrameIdx(frames)) }
+// Fixed-ray / fixed-point hooks and BVH inspection run on the first GPU (every replica holds the same scene).
+#define RT2_FIRST_RC(expr)                                           \
+  if (!r) return Fail(RT2_ERR_INVALID_ARG, "null renderer");         \
+  {                                                                  \
+    int rc__ = (expr);                                               \
+    if (rc__ != RT2_OK) return Fail(rc__, r->impl.First().Error());  \
+    return RT2_OK;                                                   \
+  }
 int rt2_intersect(rt2_renderer* r, const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out) {
   if (n > 0 && (!rays || !out)) return Fail(RT2_ERR_INVALID_ARG, "null argument");
-  RT2_FORWARD(r->impl.Intersect(rays, n, tmin, tmax, skip_media, out))
+  RT2_FIRST_RC(r->impl.First().Intersect(rays, n, tmin, tmax, skip_media, out))
+}
+int rt2_texture_value(rt2_renderer* r, uint32_t tex_idx, const float* points, const float* uv, size_t n, float* rgb) {
+  if (n > 0 && (!points || !rgb)) return Fail(RT2_ERR_INVALID_ARG, "null argument");
+  RT2_FIRST_RC(r->impl.First().TextureValue(tex_idx, points, uv, n, rgb))
 }
 int rt2_read_bvh(rt2_renderer* r, rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs, size_t max_refs, uint32_t* n_pairs,
                  uint32_t* n_refs, uint32_t* tlas_root) {
   if (!n_pairs || !n_refs || !tlas_root) return Fail(RT2_ERR_INVALID_ARG, "null argument");
-  RT2_FORWARD(r->impl.ReadBvh(nodes, max_nodes, prim_refs, max_refs, n_pairs, n_refs, tlas_root))
+  RT2_FIRST_RC(r->impl.First().ReadBvh(nodes, max_nodes, prim_refs, max_refs, n_pairs, n_refs, tlas_root))
 }
 int rt2_get_stats(rt2_renderer* r, rt2_stats* out) {
   if (!out) return Fail(RT2_ERR_INVALID_ARG, "null argument");
@@ -243,7 +273,7 @@ int rt2_set_profiling(rt2_renderer* r, int enabled) {
 }
 int rt2_stream(rt2_renderer* r, void** stream) {
   if (!r || !stream) return Fail(RT2_ERR_INVALID_ARG, "null argument");
-  *stream = r->impl.Stream();
+  *stream = r->impl.First().Stream();
   return RT2_OK;
 }
 
@@ -261,13 +291,39 @@ int rt2_tonemap_rgb8(const float* mean_rgb, int32_t width, int32_t height, uint8
 }
 
 // ---- app: headless branch of App::Run (App.cpp:81-130,157,163-174,243-248) ------------------------------------------
-int rt2_app_run(int argc, const char* const* argv, const char* settings_path, const char* data_dir) {
+int rt2_app_run(int argc_in, const char* const* argv_in, const char* settings_path, const char* data_dir) {
   rt2::AppSettings settings;
   std::string err;
   if (!settings_path) return Fail(RT2_ERR_INVALID_ARG, "settings path required");
   int rc = rt2::LoadAppSettings(settings_path, &settings, &err);
   if (rc != RT2_OK) return Fail(rc, err);
   std::string dd = data_dir ? data_dir : "data";
+  // Extensions (not in the reference): --gpus N, --spp N, --max-depth N, --seed N; everything else is the reference's argv.
+  std::vector<const char*> argv;
+  int n_gpus = -1;  // every GPU of the box
+  uint64_t seed = static_cast<uint64_t>(std::chrono::steady_clock::now().time_since_epoch().count());
+  for (int i = 0; i < argc_in; i++) {
+    const std::string a = argv_in[i] ? argv_in[i] : "";
+    auto value = [&](long long* out) {
+      if (i + 1 >= argc_in) return false;
+      char* end = nullptr;
+      *out = std::strtoll(argv_in[i + 1], &end, 10);
+      if (end == argv_in[i + 1] || *end != 0) return false;
+      i++;
+      return true;
+    };
+    long long v = 0;
+    if (i > 0 && (a == "--gpus" || a == "--spp" || a == "--max-depth" || a == "--seed")) {
+      if (!value(&v) || (a != "--seed" && v < 1)) return Fail(RT2_ERR_INVALID_ARG, a + " needs a positive integer");
+      if (a == "--gpus") n_gpus = static_cast<int>(v);
+      else if (a == "--spp") settings.num_samples = static_cast<size_t>(v);
+      else if (a == "--max-depth") settings.max_depth = static_cast<size_t>(v);
+      else seed = static_cast<uint64_t>(v);
+      continue;
+    }
+    argv.push_back(argv_in[i]);
+  }
+  const int argc = static_cast<int>(argv.size());
   // App.cpp:84-107
   std::string full_scene_path, filename;
   if (argc <= 1) {
@@ -307,11 +363,17 @@ int rt2_app_run(int argc, const char* const* argv, const char* settings_path, co
     return rc;  // App.cpp:118-120: exit(1)
   }
   for (const std::string& w : scene->host.warnings) std::fprintf(stderr, "Scene warning: %s. %s\n", w.c_str(), full_scene_path.c_str());
+  const int visible = rt2_device_count();
+  if (n_gpus > visible) {
+    rt2_scene_destroy(scene);
+    return Fail(RT2_ERR_INVALID_ARG, "--gpus " + std::to_string(n_gpus) + ": only " + std::to_string(visible) + " CUDA device(s) visible");
+  }
   rt2_config cfg{};
   cfg.device = 0;
+  cfg.n_gpus = n_gpus;
   cfg.samples_per_pixel = static_cast<int32_t>(settings.num_samples);
   cfg.max_depth = static_cast<int32_t>(settings.max_depth);
-  cfg.seed = static_cast<uint64_t>(std::chrono::steady_clock::now().time_since_epoch().count());
+  cfg.seed = seed;
   rt2_renderer* r = nullptr;
   rc = rt2_create(scene, &cfg, &r);
   if (rc != RT2_OK) {
@@ -319,18 +381,22 @@ int rt2_app_run(int argc, const char* const* argv, const char* settings_path, co
     rt2_scene_destroy(scene);
     return rc;
   }
-  // App.cpp:244-246
-  rc = rt2_update(r, static_cast<uint32_t>(settings.num_samples));
+  // App.cpp:243-248: `if (frame_idx < num_samples) Update(scene)` once per sample, then write the image.  The calls only
+  // collect frames; the GPUs trace them in wavefront batches (rt2_update).
+  const auto t0 = std::chrono::steady_clock::now();
+  for (size_t i = 0; rc == RT2_OK && i < settings.num_samples; i++) rc = rt2_update(r, 1);
   int w = 0, h = 0;
   rt2_dims(r, &w, &h);
   std::vector<float> mean(static_cast<size_t>(w) * h * 3);
   if (rc == RT2_OK) rc = rt2_read_mean_rgb32f(r, mean.data());
+  const double wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (rc == RT2_OK) {
     rt2_stats st{};
     rt2_get_stats(r, &st);
     if (st.gpu_ms_total > 0) {
-      std::printf("Rendered %llu paths, %llu rays in %.3f ms (%.1f Mrays/s)\n", static_cast<unsigned long long>(st.paths),
-                  static_cast<unsigned long long>(st.rays), st.gpu_ms_total, st.rays / st.gpu_ms_total * 1e-3);
+      std::printf("Rendered %llu paths, %llu rays on %u GPU(s) in %.3f s (render + reduce + read-back; %.1f Mrays/s)\n",
+                  static_cast<unsigned long long>(st.paths), static_cast<unsigned long long>(st.rays), st.n_gpus, wall_s,
+                  st.rays / wall_s * 1e-6);
     }
     // App.cpp:163-174
     if (!user_defined_output_path) {

@@ -173,16 +173,18 @@ class SceneLoader:
 
 
 class RayTracer:
-    """``raytrace2::cpu::RayTracer`` (src/cpu_raytrace/RayTracer.hpp:15-42) on one B200.
+    """``raytrace2::cpu::RayTracer`` (src/cpu_raytrace/RayTracer.hpp:15-42) on the B200s of one box.
 
     ``num_samples`` is ``AppSettings::num_samples`` as App.cpp:129 hands it to ``Camera::SetSamplesPerPixel``: it fixes
-    the stratification grid (sqrt(num_samples) cells per axis, RayTracer.cpp:57-60).  ``frame_offset`` / ``frame_stride``
-    select which global frames this instance traces (multi-GPU sample partition).
+    the stratification grid (sqrt(num_samples) cells per axis, RayTracer.cpp:57-60).  ``n_gpus`` > 1 (or -1 = all visible)
+    puts one replica per GPU behind this object: the frames of every ``Update`` are dealt round-robin and every read-out
+    sums the replicas over peer memory (rt2_config.n_gpus).  ``frame_offset`` / ``frame_stride`` select which global frames
+    this instance traces when the partition is done OUTSIDE (one process per GPU, ``raytrace2_b200.distributed``).
     """
 
     def __init__(self, scene: Scene, *, num_samples: int = 1, max_depth: int = 50, device: int = 0, seed: int = 0x5EED,
                  flags: int = 0, frames_per_batch: int = 0, frame_offset: int = 0, frame_stride: int = 1,
-                 dims: Optional[Tuple[int, int]] = None):
+                 dims: Optional[Tuple[int, int]] = None, n_gpus: int = 1):
         self._lib = load_library()
         self.scene = scene
         self.max_depth = max_depth
@@ -196,6 +198,7 @@ class RayTracer:
         cfg.frame_stride = frame_stride
         cfg.flags = flags
         cfg.seed = seed
+        cfg.n_gpus = n_gpus
         self._cfg = cfg
         h = C.c_void_p()
         check(self._lib.rt2_create(scene._h, C.byref(cfg), C.byref(h)))
@@ -246,6 +249,23 @@ class RayTracer:
     # ---- extras (test / measurement hooks) ----
     def synchronize(self) -> None:
         check(self._lib.rt2_synchronize(self._h))
+
+    def flush(self) -> None:
+        """Trace every frame requested by ``Update`` so far (asynchronous; ``Update`` collects frames into wavefront batches)."""
+        check(self._lib.rt2_flush(self._h))
+
+    def texture_value(self, tex_idx: int, points, uv=None) -> np.ndarray:
+        """Device ``textures[tex_idx]->Value(u, v, p)`` (Texture.cpp:7-22) for fixed points: [n, 3] float32."""
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        n = p.shape[0]
+        out = np.zeros((n, 3), np.float32)
+        uvp = None
+        if uv is not None:
+            uva = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+            assert uva.shape[0] == n
+            uvp = uva.ctypes.data_as(C.c_void_p)
+        check(self._lib.rt2_texture_value(self._h, tex_idx, p.ctypes.data_as(C.c_void_p), uvp, n, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def upload_scene(self, scene: Optional[Scene] = None) -> None:
         check(self._lib.rt2_upload_scene(self._h, (scene or self.scene)._h))

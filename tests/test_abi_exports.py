@@ -23,7 +23,7 @@ def test_header_symbols_exported(native_lib):
 
 
 def test_abi_version_and_error_string(native_lib):
-    assert native_lib.rt2_abi_version() == 2
+    assert native_lib.rt2_abi_version() == 3
     assert isinstance(native_lib.rt2_last_error(), bytes)
 
 

@@ -92,8 +92,42 @@ def _check_bvh(scene):
     roots = [int(d.tlas_root)] + [int(i["blas_root"]) for i in scene.instances()]
     for r in roots:
         walk(r, None, None, 0)
+    n_inst = len(scene.instances())
+    world_only = np.zeros(len(refs), np.int32)
+    if d.has_world_tlas:
+        # instance split: a second world tree over the same surfaces, without the instance leaves
+        assert 1 <= n_inst <= _capi.RT2_MAX_HOISTED_INSTANCES
+        before = seen.copy()
+        walk(int(d.tlas_world_root), None, None, 0)
+        world_only = seen - before
+        seen = before
+        via_tlas = sorted(int(refs[i]) for i in range(len(refs)) if before[i] and (int(refs[i]) >> 28) != _capi.RT2_PRIM_INSTANCE
+                          and i in _leaf_ref_slots(nodes, int(d.tlas_root)))
+        via_world = sorted(int(refs[i]) for i in range(len(refs)) if world_only[i])
+        assert via_tlas == via_world, "the surfaces-only world tree must hold exactly the TLAS's non-instance leaves"
+        assert all((r >> 28) != _capi.RT2_PRIM_INSTANCE for r in via_world)
+        b = np.ctypeslib.as_array(d.inst_bounds, shape=(n_inst, 8))
+        assert np.all(b[:, 0:3] < b[:, 4:7])
+    else:
+        assert n_inst == 0 or n_inst > _capi.RT2_MAX_HOISTED_INSTANCES
     for i in range(len(refs)):
-        assert seen[i] == (0 if i in media_refs else 1), f"prim ref {i} referenced {seen[i]} times"
+        assert seen[i] + world_only[i] == (0 if i in media_refs else 1), f"prim ref {i} referenced {seen[i]} times"
+
+
+def _leaf_ref_slots(nodes, root):
+    """prim_refs slots reachable from one tree."""
+    out, todo = set(), [root]
+    while todo:
+        pair = todo.pop()
+        for side in range(2):
+            n = nodes[2 * pair + side]
+            if not (n["bmin"][0] <= n["bmax"][0]):
+                continue
+            if n["count"] == 0:
+                todo.append(int(n["left_first"]))
+            else:
+                out.update(range(int(n["left_first"]), int(n["left_first"] + n["count"])))
+    return out
 
 
 @pytest.mark.parametrize("name", CURRENT_SCENES + ["final_render_book_1"])
