@@ -235,6 +235,7 @@ typedef struct rt2_renderer rt2_renderer;
 #define RT2_FLAG_SORT_RAYS 16u  /* reorder every bounce's ray queue by (direction octant, origin cell) before the traversal
                                    (device radix sort); changes the traversal ORDER only, never a result.  Measured as a net
                                    loss: compiled only into `make EXPERIMENTS=1` builds, RT2_ERR_UNSUPPORTED otherwise */
+#define RT2_FLAG_NO_FLAT_EXTEND 128u /* walk the BVH even in tiny scenes that would take the tree-less flat extend kernel (A/B) */
 #define RT2_FLAG_NO_INSTANCE_SPLIT 64u /* walk instances inline (one kernel, instance leaves in the TLAS) even when the scene
                                    qualifies for the two-pass instance split (RT2_MAX_HOISTED_INSTANCES); A/B and debugging */
 
@@ -279,6 +280,7 @@ typedef struct rt2_stats {
   uint64_t pending_frames;  /* always 0 here: rt2_get_stats traces every requested frame first */
   uint32_t n_gpus;          /* replicas behind this handle */
   uint32_t instance_split;  /* 1 iff the two-pass instance split is active */
+  double gpu_ms_extend_inst; /* instance split, while profiling: time of the instance pass (gpu_ms_extend = the world pass) */
 } rt2_stats;
 
 typedef struct rt2_hit {

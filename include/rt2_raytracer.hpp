@@ -73,6 +73,7 @@ class RayTracer {
   size_t max_depth{50};     // RayTracer::max_depth (RayTracer.hpp:32); applied at Init
   int num_samples{1};       // Camera::SetSamplesPerPixel (App.cpp:129): stratification grid
   int device{0};
+  int n_gpus{-1};           // -1: every GPU of the box behind this one object (rt2_config.n_gpus); 1: only `device`
   uint64_t seed{0x5EED};
 
   RayTracer() = default;
@@ -86,6 +87,7 @@ class RayTracer {
     r_ = nullptr;
     rt2_config cfg{};
     cfg.device = device;
+    cfg.n_gpus = n_gpus;
     cfg.samples_per_pixel = num_samples;
     cfg.max_depth = static_cast<int32_t>(max_depth);
     cfg.frame_offset = frame_offset;
@@ -93,6 +95,8 @@ class RayTracer {
     cfg.seed = seed;
     Check(rt2_create(scene.Handle(), &cfg, &r_));
   }
+  // +1 sample per pixel (RayTracer.cpp:55-70).  Cheap: frames are collected into wavefront batches and traced when a batch is
+  // full or when pixels are read, so the reference's one-Update-per-sample loop (App.cpp:244-246) needs no change.
   void Update(const Scene&) { Check(rt2_update(r_, 1)); }
   void Update(const Scene&, uint32_t n_frames) { Check(rt2_update(r_, n_frames)); }  // n x Update in one call
   void OnResize(int w, int h) { Check(rt2_resize(r_, w, h)); }

@@ -26,6 +26,7 @@ RT2_FLAG_GPU_LBVH = 8
 RT2_FLAG_SORT_RAYS = 16
 RT2_FLAG_WIDE_BVH = 32
 RT2_FLAG_NO_INSTANCE_SPLIT = 64
+RT2_FLAG_NO_FLAT_EXTEND = 128
 RT2_MAX_HOISTED_INSTANCES = 4
 RT2_ABI_VERSION = 3
 
@@ -117,7 +118,8 @@ class Stats(C.Structure):
                 ("gpu_ms_total", C.c_double), ("gpu_ms_extend", C.c_double), ("gpu_ms_shade", C.c_double),
                 ("gpu_ms_other", C.c_double), ("gpu_ms_finish", C.c_double), ("gpu_ms_bvh_build", C.c_double), ("box_pair_tests", C.c_uint64),
                 ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64), ("gpu_ms_sort", C.c_double),
-                ("stack_overflows", C.c_uint64), ("pending_frames", C.c_uint64), ("n_gpus", C.c_uint32), ("instance_split", C.c_uint32)]
+                ("stack_overflows", C.c_uint64), ("pending_frames", C.c_uint64), ("n_gpus", C.c_uint32), ("instance_split", C.c_uint32),
+                ("gpu_ms_extend_inst", C.c_double)]
 
 
 class Hit(C.Structure):

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kBlock) k_media(const DeviceScene S, const Fra
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float4 o = ray_o[i], d = ray_d[i];
-    const uint4 tr = load_closest(trav, io, i);
+    const uint4 tr = load_closest(S, trav, io, i);
     const RngKey key = key_of_slot(fp, __float_as_uint(state[i].w));
     Closest best{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)};
     int32_t mh = -1;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kBlock) k_finish_hit(const DeviceScene S, cons
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float4 o = ray_o[i], d = ray_d[i];
-    const uint4 tr = load_closest(trav, io, i);
+    const uint4 tr = load_closest(S, trav, io, i);
     const RngKey key = key_of_slot(fp, __float_as_uint(state[i].w));
     HitOut h;
     finish_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, bounce,
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
     float4 no = make_float4(0, 0, 0, 0), nd = make_float4(0, 0, 0, 0), ns = make_float4(0, 0, 0, 0);
     if (i < n) {
       const float4 o = ray_o[i], d = ray_d[i];
-      const uint4 tr = load_closest(trav, io, i);
+      const uint4 tr = load_closest(S, trav, io, i);
       const float4 st = state[i];
       const uint32_t slot = __float_as_uint(st.w);
       const RngKey key = key_of_slot(fp, slot);
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(kBlock) k_finish_intersect(const DeviceScene S
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 o = ray_o[i], d = ray_d[i];
-  const uint4 tr = load_closest(trav, io, i);
+  const uint4 tr = load_closest(S, trav, io, i);
   RngKey key{i, 0u, seed_lo, seed_hi};
   HitOut h;
   finish_hit<M>(S, make_f3(o), make_f3(d), o.w, tmin, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, 0,
@@ -992,7 +992,7 @@ int Renderer::UploadScene(const HostScene& scene) {
   d.flat_refs = nullptr;
   d.flat_offsets = nullptr;
   uint32_t flat_max = static_cast<uint32_t>(TuneInt("RT2_FLAT_MAX", kFlatMaxPrims));
-  if (TuneInt("RT2_FLAT", 1) == 0) flat_max = 0u;
+  if (TuneInt("RT2_FLAT", 1) == 0 || (cfg_.flags & RT2_FLAG_NO_FLAT_EXTEND)) flat_max = 0u;
   // (an explicit RT2_FLAG_GPU_LBVH asks for the device-built trees: keep the BVH walk)
   if (!gpu_bvh && flat_max > 0 && scene.tree_prims.size() == scene.instances.size() + 1 &&
       (scene.instances.empty() || d.inst_bounds != nullptr)) {
@@ -1325,7 +1325,7 @@ struct ExtendArgs {
 };
 
 template <class M, bool kCount>
-static void LaunchExtendT(Renderer::Impl& m, const ExtendArgs& a, uint64_t* launches) {
+static void LaunchExtendT(Renderer::Impl& m, const ExtendArgs& a, uint64_t* launches, cudaEvent_t mid) {
   if (m.wide_mode) {
     k_traverse_wide<M, kCount><<<a.grid, kBlock, 0, m.stream>>>(m.ds, m.wide, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
                                                                 a.trav, m.totals, m.trav_max_steps);
@@ -1339,6 +1339,7 @@ static void LaunchExtendT(Renderer::Impl& m, const ExtendArgs& a, uint64_t* laun
     k_traverse<M, kCount, kTravWorld><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
                                                                        a.order, a.sort_min_rays, a.trav, io, m.totals, m.trav_max_steps,
                                                                        m.trav_fetch_threshold);
+    if (mid) cudaEventRecord(mid, m.stream);  // profiling: world pass | instance pass
     k_traverse<M, kCount, kTravInst><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.entry_count, 0u, a.entry_cursor, a.ray_o, a.ray_d, a.tmin,
                                                                       a.tmax, nullptr, 0u, a.trav, io, m.totals, m.trav_max_steps,
                                                                       m.trav_fetch_threshold);
@@ -1351,13 +1352,13 @@ static void LaunchExtendT(Renderer::Impl& m, const ExtendArgs& a, uint64_t* laun
   }
 }
 
-static void LaunchExtend(Renderer::Impl& m, const ExtendArgs& a, bool exact, bool count, uint64_t* launches) {
+static void LaunchExtend(Renderer::Impl& m, const ExtendArgs& a, bool exact, bool count, uint64_t* launches, cudaEvent_t mid = nullptr) {
   if (exact) {
-    if (count) LaunchExtendT<ExactMath, true>(m, a, launches);
-    else LaunchExtendT<ExactMath, false>(m, a, launches);
+    if (count) LaunchExtendT<ExactMath, true>(m, a, launches, mid);
+    else LaunchExtendT<ExactMath, false>(m, a, launches, mid);
   } else {
-    if (count) LaunchExtendT<FastMath, true>(m, a, launches);
-    else LaunchExtendT<FastMath, false>(m, a, launches);
+    if (count) LaunchExtendT<FastMath, true>(m, a, launches, mid);
+    else LaunchExtendT<FastMath, false>(m, a, launches, mid);
   }
 }
 
@@ -1391,8 +1392,8 @@ int Renderer::RenderBatch(uint32_t n_frames) {
   const bool exact = !(cfg_.flags & RT2_FLAG_FAST_MATH);
   const uint32_t max_depth = static_cast<uint32_t>(cfg_.max_depth);
 
-  auto prof = [&](int kind) {
-    if (!profiling_) return;
+  auto prof = [&](int kind, bool record = true) -> cudaEvent_t {
+    if (!profiling_) return nullptr;
     cudaEvent_t e;
     if (prof_used_ < m.prof_events.size()) {
       e = m.prof_events[prof_used_];
@@ -1403,7 +1404,8 @@ int Renderer::RenderBatch(uint32_t n_frames) {
     }
     m.prof_kind[prof_used_] = kind;
     prof_used_++;
-    cudaEventRecord(e, m.stream);
+    if (record) cudaEventRecord(e, m.stream);
+    return e;
   };
   prof_used_ = 0;
 
@@ -1456,7 +1458,9 @@ int Renderer::RenderBatch(uint32_t n_frames) {
       ea.io = m.split;
       ea.grid = m.grid_extend;
       ea.grid_flat = m.grid_stream;
-      LaunchExtend(m, ea, exact, profiling_, &launches_);
+      // profiling: the event between the two passes of the instance split is recorded by LaunchExtend (kind 6 = instance pass)
+      cudaEvent_t mid = (m.split_mode && !m.wide_mode && !m.flat_mode) ? prof(6, false) : nullptr;
+      LaunchExtend(m, ea, exact, profiling_, &launches_, mid);
     }
     prof(3);
     const bool last = (b + 1 == max_depth);  // RayColor(depth <= 0) returns black: nothing to scatter into
@@ -1527,7 +1531,7 @@ int Renderer::RenderBatch(uint32_t n_frames) {
       float ms = 0;
       cudaEventElapsedTime(&ms, m.prof_events[i], m.prof_events[i + 1]);
       int kind = m.prof_kind[i];
-      if (kind >= 0 && kind < 6 && kind != 4) prof_ms_[kind] += ms;
+      if (kind >= 0 && kind < 7 && kind != 4) prof_ms_[kind] += ms;
     }
   }
   return RT2_OK;
@@ -2009,6 +2013,7 @@ int Renderer::GetStats(rt2_stats* out) {
   out->gpu_ms_finish = prof_ms_[3];
   out->gpu_ms_bvh_build = bvh_build_ms_;
   out->gpu_ms_sort = prof_ms_[5];
+  out->gpu_ms_extend_inst = prof_ms_[6];
   out->box_pair_tests = t[2];
   out->sphere_tests = t[3];
   out->quad_tests = t[4];

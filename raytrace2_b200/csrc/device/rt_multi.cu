@@ -316,6 +316,7 @@ int MultiRenderer::GetStats(rt2_stats* out) {
     out->gpu_ms_other = std::max(out->gpu_ms_other, s.gpu_ms_other);
     out->gpu_ms_finish = std::max(out->gpu_ms_finish, s.gpu_ms_finish);
     out->gpu_ms_sort = std::max(out->gpu_ms_sort, s.gpu_ms_sort);
+    out->gpu_ms_extend_inst = std::max(out->gpu_ms_extend_inst, s.gpu_ms_extend_inst);
     out->gpu_ms_bvh_build = std::max(out->gpu_ms_bvh_build, s.gpu_ms_bvh_build);
     out->instance_split = s.instance_split;
   }

@@ -79,7 +79,7 @@ class Renderer {
   uint32_t n_textures_{0};
   uint64_t launches_{0};
   double gpu_ms_total_{0};
-  double prof_ms_[6]{0, 0, 0, 0, 0, 0};
+  double prof_ms_[7]{0, 0, 0, 0, 0, 0, 0};
   bool profiling_{false};
   bool timing_pending_{false};
   size_t prof_used_{0};

@@ -6,14 +6,18 @@
 
 namespace rt2dev {
 
-// PerlinInterp (PerlinNoiseGen.cpp:10-26)
+// PerlinNoiseGen::Noise + PerlinInterp (PerlinNoiseGen.cpp:10-26,66-88), operation by operation in the reference's order and
+// without FMA contraction (ExactMath), so that with the same tables the value is the reference's bit for bit — which is what
+// lets rt2_texture_value be checked at fixed points (the marble's sin() then sees the same argument; sinf vs libm is the
+// only difference left).  The weights i*uu + (1-i)*(1-uu) reduce exactly to uu / 1-uu.
 __device__ __forceinline__ float perlin_noise(const rt2_perlin* __restrict__ P, F3 p) {
-  float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
-  float u = p.x - fx, v = p.y - fy, w = p.z - fz;
-  int i = static_cast<int>(fx), j = static_cast<int>(fy), k = static_cast<int>(fz);
-  float uu = u * u * (3.0f - 2.0f * u);
-  float vv = v * v * (3.0f - 2.0f * v);
-  float ww = w * w * (3.0f - 2.0f * w);
+  using E = ExactMath;
+  const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+  const float u = E::sub(p.x, fx), v = E::sub(p.y, fy), w = E::sub(p.z, fz);
+  const int i = static_cast<int>(fx), j = static_cast<int>(fy), k = static_cast<int>(fz);
+  const float uu = E::mul(E::mul(u, u), E::sub(3.0f, E::mul(2.0f, u)));
+  const float vv = E::mul(E::mul(v, v), E::sub(3.0f, E::mul(2.0f, v)));
+  const float ww = E::mul(E::mul(w, w), E::sub(3.0f, E::mul(2.0f, w)));
   float accum = 0.0f;
 #pragma unroll
   for (int di = 0; di < 2; di++) {
@@ -25,9 +29,10 @@ __device__ __forceinline__ float perlin_noise(const rt2_perlin* __restrict__ P, 
       for (int dk = 0; dk < 2; dk++) {
         const int pz = __ldg(&P->perm_z[(k + dk) & 255]);
         const float4 c = __ldg(reinterpret_cast<const float4*>(&P->vec[(px ^ py ^ pz) & 255][0]));
-        float wx = u - di, wy = v - dj, wz = w - dk;
-        float weight = (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww);
-        accum += weight * ((c.x * wx + c.y * wy) + c.z * wz);
+        const float wx = E::sub(u, static_cast<float>(di)), wy = E::sub(v, static_cast<float>(dj)), wz = E::sub(w, static_cast<float>(dk));
+        const float a = di ? uu : E::sub(1.0f, uu), b = dj ? vv : E::sub(1.0f, vv), cc = dk ? ww : E::sub(1.0f, ww);
+        const float dot = E::add(E::add(E::mul(c.x, wx), E::mul(c.y, wy)), E::mul(c.z, wz));  // glm::dot
+        accum = E::add(accum, E::mul(E::mul(E::mul(a, b), cc), dot));
       }
     }
   }
@@ -38,7 +43,7 @@ __device__ __forceinline__ float perlin_noise(const rt2_perlin* __restrict__ P, 
 __device__ __forceinline__ float perlin_turb(const rt2_perlin* __restrict__ P, F3 p) {
   float accum = 0.0f, weight = 1.0f;
   for (int i = 0; i < 7; i++) {
-    accum += weight * perlin_noise(P, p);
+    accum = ExactMath::add(accum, ExactMath::mul(weight, perlin_noise(P, p)));
     weight *= 0.5f;
     p = {p.x * 2.0f, p.y * 2.0f, p.z * 2.0f};
   }
@@ -83,12 +88,13 @@ __device__ __forceinline__ F3 texture_value(const DeviceScene& S, uint32_t tex_i
       const float4 t2 = __ldg(S.textures + 3 * tex_idx + 2);
       const rt2_perlin* P = S.perlin + __float_as_uint(t0.w);
       float f;
+      // Texture.cpp:16-22: albedo * 0.5 * (1 + noise(scale * p))  |  albedo * 0.5 * (1 + sin(scale * p.z + 10 * turb(p)))
       if (__float_as_uint(t2.x) == 0u) {  // NoiseType::kPerlin
-        f = 0.5f * (1.0f + perlin_noise(P, F3{t1.w * p.x, t1.w * p.y, t1.w * p.z}));
+        f = ExactMath::add(1.0f, perlin_noise(P, F3{ExactMath::mul(t1.w, p.x), ExactMath::mul(t1.w, p.y), ExactMath::mul(t1.w, p.z)}));
       } else {  // kMarble
-        f = 0.5f * (1.0f + sinf(t1.w * p.z + 10.0f * perlin_turb(P, p)));
+        f = ExactMath::add(1.0f, sinf(ExactMath::add(ExactMath::mul(t1.w, p.z), ExactMath::mul(10.0f, perlin_turb(P, p)))));
       }
-      return {t1.x * f, t1.y * f, t1.z * f};
+      return {ExactMath::mul(ExactMath::mul(t1.x, 0.5f), f), ExactMath::mul(ExactMath::mul(t1.y, 0.5f), f), ExactMath::mul(ExactMath::mul(t1.z, 0.5f), f)};
     }
     return {t1.x, t1.y, t1.z};  // solid colour
   }

@@ -282,18 +282,23 @@ __device__ __forceinline__ float from_ordered_bits(uint32_t k) {
 }
 
 // The closest SURFACE of ray i after the extend kernels: the world pass's record, replaced by the best instance entry of
-// the ray when that one is closer (strictly: an exact tie keeps the world-space primitive).
-__device__ __forceinline__ uint4 load_closest(const uint4* __restrict__ trav, const SplitIO& io, uint32_t i) {
+// the ray when that one is closer — or exactly as close and the winner of the reference's tie rule (quad_wins_tie: the
+// ranks are global, so the rule does not care which space a quad lives in).
+__device__ __forceinline__ uint4 load_closest(const DeviceScene& S, const uint4* __restrict__ trav, const SplitIO& io, uint32_t i) {
   uint4 tr = trav[i];
   if (tr.w != 0u) {
     const unsigned long long b = io.inst_best[i];
     if (b != ~0ull) {
       const float t = from_ordered_bits(static_cast<uint32_t>(b >> 32));
-      if (t < __uint_as_float(tr.x)) {
+      const float tw = __uint_as_float(tr.x);
+      if (t <= tw) {
         const uint32_t e = static_cast<uint32_t>(b);
-        tr.x = __float_as_uint(t);
-        tr.y = io.entry_prim[e];
-        tr.z = io.entries[e].y;
+        const uint32_t prim = io.entry_prim[e];
+        if (t < tw || (RT2_PRIM_TYPE(prim) == RT2_PRIM_QUAD && quad_wins_tie(S, t, prim, Closest{tw, tr.y, -1}))) {
+          tr.x = __float_as_uint(t);
+          tr.y = prim;
+          tr.z = io.entries[e].y;
+        }
       }
     }
     tr.w = 0u;

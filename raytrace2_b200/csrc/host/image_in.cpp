@@ -64,14 +64,21 @@ bool DecodePPM(const std::vector<uint8_t>& d, int* w, int* h, std::vector<uint8_
   rgb->resize(static_cast<size_t>(W) * H * 3);
   const size_t n = rgb->size();
   if (binary) {
-    c.p++;  // single whitespace after maxval
+    // exactly one whitespace byte follows maxval; a file that ends right after the header has none
+    if (c.p >= c.end) {
+      *err = "truncated PPM";
+      return false;
+    }
+    c.p++;
     const size_t bytes = maxv > 255 ? 2 : 1;
-    if (static_cast<size_t>(c.end - c.p) < n * bytes) {
+    const long long remaining = static_cast<long long>(c.end - c.p);
+    if (remaining < 0 || static_cast<unsigned long long>(remaining) < static_cast<unsigned long long>(n) * bytes) {
       *err = "truncated PPM";
       return false;
     }
     for (size_t i = 0; i < n; i++) {
       long v = bytes == 2 ? (c.p[2 * i] << 8 | c.p[2 * i + 1]) : c.p[i];
+      if (v > maxv) v = maxv;  // like the P3 path
       (*rgb)[i] = static_cast<uint8_t>((v * 255 + maxv / 2) / maxv);
     }
   } else {

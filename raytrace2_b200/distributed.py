@@ -61,8 +61,11 @@ class DistributedRayTracer:
         if backend == "nccl":
             ptr, n = self.tracer.accum_device_ptr()
             self.tracer.synchronize()
-            t = torch.as_tensor(_CudaBuffer(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
-            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM, group=self.group)  # in place on the renderer's accumulator
+            acc = torch.as_tensor(_CudaBuffer(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
+            # Reduce a COPY: the renderer's accumulator must keep holding this rank's frames only, or a second read-out, a later
+            # Update + read-out, resolve_p2p() or a checkpoint on rank 0 would count the other ranks' frames twice.
+            t = acc.clone()
+            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM, group=self.group)
             torch.cuda.synchronize()
             if self.rank != 0:
                 return None

@@ -38,21 +38,13 @@ def test_medium_only_scene(native_lib):
     assert tr.stats()["rays"] > tr.stats()["paths"]
 
 
-@pytest.mark.parametrize("flat", ["1", "0"])
-def test_single_primitive_and_depth_one(native_lib, flat):
-    old = os.environ.get("RT2_FLAT")
-    os.environ["RT2_FLAT"] = flat
-    try:
-        b = sb.SceneBuilder(width=64, fov=40, center=(0, 0, 5), look_at=(0, 0, 0), background=(0.5, 0.7, 1.0))
-        b.place(b.sphere((0, 0, 0), 1.0, b.lambertian((0.8, 0.8, 0.8))))
-        scene = rt.Scene.from_builder(b)
-        deep = rt.RayTracer(scene, num_samples=16, seed=5, max_depth=50)
-        one = rt.RayTracer(scene, num_samples=16, seed=5, max_depth=1)
-    finally:
-        if old is None:
-            os.environ.pop("RT2_FLAT", None)
-        else:
-            os.environ["RT2_FLAT"] = old
+@pytest.mark.parametrize("flags", [0, rt.RT2_FLAG_NO_FLAT_EXTEND])
+def test_single_primitive_and_depth_one(native_lib, flags):
+    b = sb.SceneBuilder(width=64, fov=40, center=(0, 0, 5), look_at=(0, 0, 0), background=(0.5, 0.7, 1.0))
+    b.place(b.sphere((0, 0, 0), 1.0, b.lambertian((0.8, 0.8, 0.8))))
+    scene = rt.Scene.from_builder(b)
+    deep = rt.RayTracer(scene, num_samples=16, seed=5, max_depth=50, flags=flags)
+    one = rt.RayTracer(scene, num_samples=16, seed=5, max_depth=1, flags=flags)
     deep.Update(16)
     one.Update(16)
     a, c = deep.NonConvertedPixels(), one.NonConvertedPixels()

@@ -78,6 +78,8 @@ def test_device_built_tree_is_valid_and_gives_identical_hits(native_lib, name):
                     total += int(nd["count"])
         return total
     sizes = [count_leaves(d.tlas_root)] + [count_leaves(int(i["blas_root"])) for i in scene.instances()]
+    if d.has_world_tlas:  # instance split: one more world tree over the surfaces only, laid out last
+        sizes.append(count_leaves(d.tlas_world_root))
     roots, base = [], 0
     for n in sizes:
         roots.append(base)

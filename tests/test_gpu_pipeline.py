@@ -15,18 +15,9 @@ from _rays import fixed_rays
 pytestmark = pytest.mark.gpu
 
 
-def _render(name, dims, spp, flags=0, env=None, fpb=0, seed=77):
-    old = {k: os.environ.get(k) for k in (env or {})}
-    os.environ.update(env or {})
-    try:
-        scene = rt.Scene.load(scene_path(name), perlin_seed=5)
-        tr = rt.RayTracer(scene, num_samples=spp, max_depth=50, seed=seed, flags=flags, dims=dims, frames_per_batch=fpb)
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
+def _render(name, dims, spp, flags=0, fpb=0, seed=77):
+    scene = rt.Scene.load(scene_path(name), perlin_seed=5)
+    tr = rt.RayTracer(scene, num_samples=spp, max_depth=50, seed=seed, flags=flags, dims=dims, frames_per_batch=fpb)
     tr.Update(spp)
     return tr, tr.read_accum()
 
@@ -45,31 +36,28 @@ def test_fused_and_per_bin_pipelines_trace_the_same_paths(native_lib, name, dims
 
 
 def test_sorted_queue_renders_the_same_image(native_lib):
+    """The ray sort measured as a net loss (profiles/r01_notes.md) and lives only in `make EXPERIMENTS=1` builds: the shipped
+    library must reject the flag loudly; an experiments build must render the same image with and without it."""
     name, dims, spp = "book2_final_scene_10000_samples", (256, 256), 16
     _, a = _render(name, dims, spp)
-    tb, b = _render(name, dims, spp, flags=rt.RT2_FLAG_SORT_RAYS, env={"RT2_SORT_MIN": "1000"})
+    try:
+        tb, b = _render(name, dims, spp, flags=rt.RT2_FLAG_SORT_RAYS)
+    except rt.Rt2Error as e:
+        assert e.code == -5 and "EXPERIMENTS" in e.message
+        return
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
-    _, u = _render(name, dims, spp, flags=rt.RT2_FLAG_NO_FUSED_SHADE)
-    _, c = _render(name, dims, spp, flags=rt.RT2_FLAG_SORT_RAYS | rt.RT2_FLAG_NO_FUSED_SHADE, env={"RT2_SORT_MIN": "1000"})
-    assert np.array_equal(u.view(np.uint32), c.view(np.uint32))
 
 
 @pytest.mark.parametrize("name", ["cornell_original_test", "cornell_box_scene_graph", "cornell_volume_10000_samples"])
 def test_flat_and_bvh_extend_agree(native_lib, name):
-    """Tiny scenes take k_traverse_flat; the BVH walk (RT2_FLAT=0) must report the same t bit for bit and the same primitive
+    """Tiny scenes take k_traverse_flat; the BVH walk (RT2_FLAG_NO_FLAT_EXTEND) must report the same t bit for bit and the same primitive
     except on exact ties between coincident faces (resolved by test order)."""
     scene = rt.Scene.load(scene_path(name))
     o, d, _ = fixed_rays(scene, 60000, seed=9)
     tf = rt.RayTracer(scene, dims=(64, 64))
-    old = os.environ.get("RT2_FLAT")
-    os.environ["RT2_FLAT"] = "0"
-    try:
-        tb = rt.RayTracer(scene, dims=(64, 64))
-    finally:
-        if old is None:
-            os.environ.pop("RT2_FLAT", None)
-        else:
-            os.environ["RT2_FLAT"] = old
+    tb = rt.RayTracer(scene, dims=(64, 64), flags=rt.RT2_FLAG_NO_FLAT_EXTEND)  # 2 instances: the two-pass instance split
+    n_inst = len(scene.instances())  # the Cornell boxes are instances; box-bounded media under a transform are not
+    assert tb.stats()["instance_split"] == (1 if 1 <= n_inst <= 4 else 0) and tf.stats()["instance_split"] == 0
     f = tf.intersect(o, d, skip_media=True)
     b = tb.intersect(o, d, skip_media=True)
     assert np.array_equal(f["material"] >= 0, b["material"] >= 0)
@@ -77,7 +65,7 @@ def test_flat_and_bvh_extend_agree(native_lib, name):
     assert hit.sum() > 10000
     assert np.array_equal(f["t"][hit].view(np.uint32), b["t"][hit].view(np.uint32))
     same = (f["prim"][hit] == b["prim"][hit]) & (f["instance"][hit] == b["instance"][hit])
-    assert same.mean() > 0.95
+    assert same.mean() > 0.999  # ties follow the reference's rule in both kernels (quad_wins_tie)
     # the render kernels: statistically the same image is checked against the oracle elsewhere; here the ray counts
     tf.Update(4)
     tb.Update(4)

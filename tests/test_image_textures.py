@@ -45,6 +45,22 @@ def test_ascii_ppm_and_missing_file(native_lib, tmp_path):
     assert cyan.shape == (1, 1, 4) and np.array_equal(cyan[0, 0, :3], [0, 1, 1])
 
 
+def test_truncated_and_out_of_range_binary_ppm(native_lib, tmp_path):
+    """A P6 file that ends right after its header (or short of pixels) must be rejected, not read out of bounds; 16-bit samples
+    above maxval are clamped like in the ASCII path."""
+    (tmp_path / "hdr_only.ppm").write_bytes(b"P6 4 4 255")
+    (tmp_path / "short.ppm").write_bytes(b"P6\n4 4\n255\n" + bytes(10))
+    for name in ("hdr_only.ppm", "short.ppm"):
+        got = _scene_with(name, tmp_path).images()[0]  # undecodable -> the 1x1 cyan debugging texture, like a missing file
+        assert got.shape == (1, 1, 4) and np.array_equal(got[0, 0, :3], [0, 1, 1])
+    # maxval 1000, one sample of 2000 (> maxval) and one of 500
+    body = b"".join(int(v).to_bytes(2, "big") for v in (2000, 500, 0))
+    (tmp_path / "clamp.ppm").write_bytes(b"P6\n1 1\n1000\n" + body)
+    got = _scene_with("clamp.ppm", tmp_path).images()[0]
+    assert got.shape == (1, 1, 4)
+    assert np.allclose(got[0, 0, :3], _lin(np.array([255, 128, 0], np.uint8)), rtol=2e-6, atol=1e-7)
+
+
 def test_restatement_lookup_rule(port_oracle, tmp_path):
     from PIL import Image
     pic = make_picture()

@@ -30,6 +30,12 @@ p2p8 = drt.resolve_p2p(rgba8=True)
 t0 = time.perf_counter()
 img = drt.NonConvertedPixels()
 t_nccl = time.perf_counter() - t0
+# the NCCL read-out reduces a copy: a second read-out and a peer-memory read-out afterwards must see the same accumulators
+img_again = drt.NonConvertedPixels()
+p2p_again = drt.resolve_p2p()
+if rank == 0:
+    assert np.array_equal(img, img_again), "a second NCCL read-out must not double-count rank 0's frames"
+    assert np.array_equal(p2p, p2p_again), "the NCCL read-out must leave the renderer's accumulator untouched"
 if rank == 0:
     d = np.abs(p2p - img).max() / max(img.max(), 1e-9)
     print(f"dist_check: P2P resolve vs NCCL reduce: max rel diff {d:.3e}; wall {t_p2p * 1e3:.2f} ms vs {t_nccl * 1e3:.2f} ms (incl. barriers / host copy)")
