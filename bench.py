@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scene", default=DEFAULT_SCENE, help="scene name under data/ (or 'synthetic:<n_spheres>')")
-    ap.add_argument("--spp-per-step", type=int, default=0, help="samples per pixel per step = one wavefront batch (0 = ~92 M paths: 256 at 600x600)")
+    ap.add_argument("--spp-per-step", type=int, default=0, help="samples per pixel per step = one wavefront batch (0 = ~184 M paths: 512 at 600x600)")
     ap.add_argument("--spp-total", type=int, default=10000, help="samples-per-pixel setting (fixes the stratification grid)")
     ap.add_argument("--max-depth", type=int, default=50)
     ap.add_argument("--width", type=int, default=0)
@@ -187,7 +187,7 @@ def run_reference(args):
         return 0
     threads = os.cpu_count() or 1
     dims = (args.width, args.height) if args.width and args.height else None
-    spp = max(1, (args.spp_per_step or 256) // 32)  # bounded sample per step: the CPU is ~600x slower than one B200
+    spp = max(1, (args.spp_per_step or 512) // 64)  # bounded sample per step: the CPU is ~700x slower than one B200
     if is_synthetic(args.scene):
         print(json.dumps({"impl": "reference", "unavailable": "the synthetic scene has no JSON file the reference could load"}))
         return 0
@@ -256,7 +256,8 @@ def accum_tensor(torch, tracer, dev):
 
 
 def auto_spp_per_step(w, h):
-    return max(1, min(256, (96 * 1024 * 1024 + w * h - 1) // (w * h)))
+    """One wavefront batch of the library's default size: ~192 M paths (Renderer::AllocState)."""
+    return max(1, min(512, (192 * 1024 * 1024 + w * h - 1) // (w * h)))
 
 
 def time_config(rt, torch, D, args, name, dims, spp_step, steps=2, warmup=1):

@@ -276,11 +276,15 @@ typedef struct rt2_stats {
   uint64_t quad_tests;
   uint64_t instance_visits;
   double gpu_ms_sort; /* ... of the ray-sort kernels (RT2_FLAG_SORT_RAYS) */
-  uint64_t stack_overflows; /* warps whose traversal found the 64-entry stack full (0 in a valid render; read-outs fail otherwise) */
+  uint64_t stack_overflows; /* warps whose traversal found its stack full (wide-BVH walk only; the binary walks cannot overflow:
+                               rt2_create / rt2_upload_scene refuse a scene whose trees are deeper than the stack).  0 in a
+                               valid render; read-outs fail otherwise */
   uint64_t pending_frames;  /* always 0 here: rt2_get_stats traces every requested frame first */
   uint32_t n_gpus;          /* replicas behind this handle */
   uint32_t instance_split;  /* 1 iff the two-pass instance split is active */
   double gpu_ms_extend_inst; /* instance split, while profiling: time of the instance pass (gpu_ms_extend = the world pass) */
+  uint32_t max_stack_need;  /* stack entries the deepest traversal of this scene can need (tree depths, verified <= 63 at upload) */
+  uint32_t reserved;
 } rt2_stats;
 
 typedef struct rt2_hit {

@@ -119,7 +119,7 @@ class Stats(C.Structure):
                 ("gpu_ms_other", C.c_double), ("gpu_ms_finish", C.c_double), ("gpu_ms_bvh_build", C.c_double), ("box_pair_tests", C.c_uint64),
                 ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64), ("gpu_ms_sort", C.c_double),
                 ("stack_overflows", C.c_uint64), ("pending_frames", C.c_uint64), ("n_gpus", C.c_uint32), ("instance_split", C.c_uint32),
-                ("gpu_ms_extend_inst", C.c_double)]
+                ("gpu_ms_extend_inst", C.c_double), ("max_stack_need", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Hit(C.Structure):

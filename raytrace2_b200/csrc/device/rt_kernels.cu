@@ -252,8 +252,11 @@ __global__ void __launch_bounds__(kBlock) k_finish_hit(const DeviceScene S, cons
 // hit0 / hit1 and their index pushed into the material bin; k_shade_scatter / k_shade_terminal then run on those bins
 // only, so one marble ray does not stall its 31 warp-mates.
 //   counters[0] = queue size; counters[1..6] = deferred bins; next_counters[0] = rays emitted inline so far.
-template <class M, int kMinBlocks = 4, bool kMedia = true>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const DeviceScene S, const FrameParams fp, uint32_t bounce, int emit_next,
+// kMedia: 0 = no media code (none in the scene, or k_media ran first), 1 = "simple" media (one-primitive world-space
+// boundaries: book 2), 2 = general
+// kImages: the scene has image textures (HitRecord::uv and the texel lookup are compiled in)
+template <class M, int kMinBlocks = 4, int kMedia = 2, bool kImages = true, int kTile = kBlock>
+__global__ void __launch_bounds__(kTile, kMinBlocks) k_finish_shade(const DeviceScene S, const FrameParams fp, uint32_t bounce, int emit_next,
                                                          uint32_t* __restrict__ counters, uint32_t* __restrict__ next_counters,
                                                          const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                          const float4* __restrict__ state, const uint4* __restrict__ trav,
@@ -263,14 +266,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
                                                          float4* __restrict__ radiance) {
   const uint32_t n = counters[0];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  constexpr int kWarps = kBlock / 32;
+  constexpr int kWarps = kTile / 32;
   constexpr int kClasses = 5;  // lambertian, textured lambertian, metal, dielectric, isotropic
   __shared__ uint32_t s_off[2][kClasses][kWarps];
   __shared__ uint32_t s_base[2];
   int parity = 0;
-  const uint32_t n_tiles = (n + kBlock - 1) / kBlock;
+  const uint32_t n_tiles = (n + kTile - 1) / kTile;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {  // block-uniform trip count
-    const uint32_t i = tile * kBlock + threadIdx.x;
+    const uint32_t i = tile * kTile + threadIdx.x;
     bool emit = false;
     int cls = 0;
     float4 no = make_float4(0, 0, 0, 0), nd = make_float4(0, 0, 0, 0), ns = make_float4(0, 0, 0, 0);
@@ -282,8 +285,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
       const RngKey key = key_of_slot(fp, slot);
       HitOut h;
       if (kMedia) {
-        finish_hit<M>(S, make_f3(o), make_f3(d), o.w, 0.001f, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key, bounce,
-                      false, h);
+        finish_hit<M, kMedia == 1, kImages>(S, make_f3(o), make_f3(d), o.w, 0.001f, Closest{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)}, key,
+                                   bounce, false, h);
       } else {
         // no media in the scene, or k_media ran before: a medium that won left its reference in the traversal record
         Closest best{__uint_as_float(tr.x), tr.y, static_cast<int32_t>(tr.z)};
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
           mh = static_cast<int32_t>(RT2_PRIM_INDEX(tr.y));
           best.prim = RT2_PRIM_NONE;
         }
-        finish_record<M>(S, make_f3(o), make_f3(d), o.w, best, mh, h);
+        finish_record<M, false, kImages>(S, make_f3(o), make_f3(d), o.w, best, mh, h);
       }
       if (h.material < 0) {
         // miss: T * background (RayTracer.cpp:25-27)
@@ -306,28 +309,35 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) k_finish_shade(const Devic
           hit1[i] = make_float4(h.n.x, h.n.y, h.n.z, __uint_as_float(static_cast<uint32_t>(h.material) | (h.front_face ? 0x80000000u : 0u)));
           bin_push(counters, bins.base, bins.stride, bin_of_material(S, h.material), i);
         } else if (type == RT2_MAT_DIFFUSE_LIGHT) {
-          const F3 c = texture_value_simple(S, __float_as_uint(m0.y), h.p, h.u, h.v);  // DiffuseLight::Emit (Material.cpp:71-74)
+          const F3 c = texture_value_simple<kImages>(S, __float_as_uint(m0.y), h.p, h.u, h.v);  // DiffuseLight::Emit (Material.cpp:71-74)
           radiance[slot] = make_float4(st.x * c.x, st.y * c.y, st.z * c.z, 0.0f);
         } else if (emit_next) {
           const uint4 r = rng_draw(key, bounce, kStreamScatter);
           F3 dir, att;
-          if (type == RT2_MAT_LAMBERTIAN || type == RT2_MAT_TEXTURE) {
-            // Material.cpp:47-69
-            const F3 u = unit_vector(u01(r.x), u01(r.y));
-            dir = {h.n.x + u.x, h.n.y + u.y, h.n.z + u.z};
-            if (near_zero(dir)) dir = h.n;
-            att = (type == RT2_MAT_LAMBERTIAN) ? F3{m1.x, m1.y, m1.z} : texture_value_simple(S, __float_as_uint(m0.y), h.p, h.u, h.v);
-            cls = (type == RT2_MAT_LAMBERTIAN) ? 0 : 1;
-          } else if (type == RT2_MAT_METAL) {
-            att = scatter<RT2_MAT_METAL>(S, m0, m1, make_f3(d), h.p, h.n, h.front_face, r, dir);
-            cls = 2;
-          } else if (type == RT2_MAT_DIELECTRIC) {
+          if (type == RT2_MAT_DIELECTRIC) {
             att = scatter<RT2_MAT_DIELECTRIC>(S, m0, m1, make_f3(d), h.p, h.n, h.front_face, r, dir);
             cls = 3;
-          } else {  // RT2_MAT_ISOTROPIC, Material.cpp:76-83
-            cls = 4;
-            dir = unit_vector(u01(r.x), u01(r.y));
-            att = texture_value_simple(S, __float_as_uint(m0.y), h.p, h.u, h.v);
+          } else {
+            // every other material scatters around one uniform direction (math::RandUnitVec3): ONE copy of the sincos code
+            const F3 u = unit_vector(u01(r.x), u01(r.y));
+            if (type == RT2_MAT_METAL) {
+              // Material.cpp:10-17: always scatters (no dot(scattered, normal) > 0 test)
+              const F3 refl = normalize3(reflect3(make_f3(d), h.n));
+              dir = {refl.x + m0.z * u.x, refl.y + m0.z * u.y, refl.z + m0.z * u.z};
+              att = {m1.x, m1.y, m1.z};
+              cls = 2;
+            } else if (type == RT2_MAT_ISOTROPIC) {
+              // Material.cpp:76-83
+              dir = u;
+              att = texture_value_simple<kImages>(S, __float_as_uint(m0.y), h.p, h.u, h.v);
+              cls = 4;
+            } else {
+              // lambertian / textured lambertian, Material.cpp:47-69
+              dir = {h.n.x + u.x, h.n.y + u.y, h.n.z + u.z};
+              if (near_zero(dir)) dir = h.n;
+              att = (type == RT2_MAT_LAMBERTIAN) ? F3{m1.x, m1.y, m1.z} : texture_value_simple<kImages>(S, __float_as_uint(m0.y), h.p, h.u, h.v);
+              cls = (type == RT2_MAT_LAMBERTIAN) ? 0 : 1;
+            }
           }
           emit = true;
           no = make_float4(h.p.x, h.p.y, h.p.z, o.w);
@@ -646,6 +656,7 @@ struct Renderer::Impl {
   uint32_t* sort_hist{nullptr};
   uint32_t* sort_bin_base{nullptr};
   int grid_sort{0};
+  bool simple_media{false};  // every medium: one-primitive boundary, no instance chain (k_finish_shade<.., kMedia = 1>)
   int trav_max_steps{8};  // node steps per round of the while-while traversal (measured: +12 % on the 1M-sphere scene, +1 % on book 2)
   int trav_fetch_threshold{kFetchThreshold};
   bool fused{true};               // k_finish_shade instead of k_finish_hit + per-bin shade kernels
@@ -903,6 +914,27 @@ int Renderer::UploadScene(const HostScene& scene) {
     }
     n_node_pairs_ = static_cast<uint32_t>(scene.nodes.size() / 2);
     n_prim_refs_ = static_cast<uint32_t>(scene.prim_refs.size());
+    {
+      // depth of every host tree in node pairs: [0] TLAS, [1 + i] BLAS of instance i, (last) surfaces-only world tree
+      auto depth_of = [&](uint32_t root) {
+        uint32_t best = 0;
+        std::vector<std::pair<uint32_t, uint32_t>> todo{{root, 1u}};
+        while (!todo.empty()) {
+          const auto [pair, depth] = todo.back();
+          todo.pop_back();
+          best = std::max(best, depth);
+          for (int side = 0; side < 2; side++) {
+            const rt2_bvh_node& nd = scene.nodes[2ull * pair + side];
+            if (nd.count == 0 && nd.bmin[0] <= nd.bmax[0]) todo.emplace_back(nd.left_first, depth + 1);
+          }
+        }
+        return best;
+      };
+      tree_depths_.clear();
+      tree_depths_.push_back(depth_of(scene.tlas_root));
+      for (const rt2_instance& in : scene.instances) tree_depths_.push_back(depth_of(in.blas_root));
+      if (scene.has_world_tlas) tree_depths_.push_back(depth_of(scene.tlas_world_root));
+    }
     world_tree_ok_ = scene.has_world_tlas;
     world_root_ = scene.tlas_world_root;
     bvh_build_ms_ = 0;
@@ -974,7 +1006,12 @@ int Renderer::UploadScene(const HostScene& scene) {
     }
   }
   m.split_media = false;
-  for (const rt2_medium& md : scene.media) m.split_media = m.split_media || md.boundary_count > 1;
+  m.simple_media = !scene.media.empty();
+  for (const rt2_medium& md : scene.media) {
+    m.split_media = m.split_media || md.boundary_count > 1;
+    m.simple_media = m.simple_media && md.boundary_count == 1 && md.chain_len == 0;
+  }
+  if (TuneInt("RT2_SIMPLE_MEDIA", 1) == 0) m.simple_media = false;
   if (TuneInt("RT2_SPLIT_MEDIA", -1) >= 0) m.split_media = !scene.media.empty() && TuneInt("RT2_SPLIT_MEDIA", 0) != 0;
   // conservative world boxes of the instances (flat mode and instance split)
   d.inst_bounds = nullptr;
@@ -1034,6 +1071,21 @@ int Renderer::UploadScene(const HostScene& scene) {
                  !scene.instances.empty() && scene.instances.size() <= kMaxHoistedInstances && d.inst_bounds != nullptr;
   d.n_hoisted = m.split_mode ? static_cast<uint32_t>(scene.instances.size()) : 0u;
   d.tlas_world_root = m.split_mode ? world_root_ : d.tlas_root;
+  {
+    // The traversal keeps one stack entry per level of the tree it walks and does no bounds checks (rt_trace.cuh): refuse a
+    // scene whose trees do not fit instead of dropping sub-trees or writing outside the stack.
+    const size_t n_inst = scene.instances.size();
+    uint32_t blas_max = 0;
+    for (size_t i = 0; i < n_inst && 1 + i < tree_depths_.size(); i++) blas_max = std::max(blas_max, tree_depths_[1 + i]);
+    const uint32_t tlas = tree_depths_.empty() ? 0u : tree_depths_[0];
+    const uint32_t world = (world_tree_ok_ && tree_depths_.size() == n_inst + 2) ? tree_depths_.back() : 0u;
+    max_stack_need_ = m.split_mode ? std::max(world, blas_max) : (n_inst ? tlas + 1 + blas_max : tlas);
+    if (max_stack_need_ > static_cast<uint32_t>(kStackSize - 1) && !m.flat_mode && !m.wide_mode) {
+      err_ = "BVH too deep for the traversal stack: needs " + std::to_string(max_stack_need_) + " entries, the stack holds " +
+             std::to_string(kStackSize - 1);
+      return RT2_ERR_UNSUPPORTED;
+    }
+  }
   if (m.split_mode && (!was_split || !m.split.entries) && width_ > 0) {
     rc = AllocSplitState();  // a re-upload switched the renderer into split mode after Resize
     if (rc != RT2_OK) return rc;
@@ -1113,6 +1165,9 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
   rc = ensure(&m.d_build_prims, &m.cap_build_prims, max_n * sizeof(BuildPrim));
   if (rc != RT2_OK) return rc;
   if (!prefix.empty()) RT2_CUDA(cudaMemcpyAsync(m.d_prim_refs, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, m.stream));
+  uint32_t* d_depths = nullptr;
+  RT2_CUDA(cudaMalloc(&d_depths, n_trees * sizeof(uint32_t)));
+  RT2_CUDA(cudaMemsetAsync(d_depths, 0, n_trees * sizeof(uint32_t), m.stream));
   RT2_CUDA(cudaEventRecord(m.ev_start, m.stream));
   for (size_t k = 0; k < n_trees; k++) {
     const std::vector<BuildPrim>& tp = *trees[k];
@@ -1120,8 +1175,11 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
       RT2_CUDA(cudaMemcpyAsync(m.d_build_prims, tp.data(), tp.size() * sizeof(BuildPrim), cudaMemcpyHostToDevice, m.stream));
     }
     rc = BuildLbvhOnDevice(static_cast<const BuildPrim*>(m.d_build_prims), static_cast<uint32_t>(tp.size()), pair_base[k], ref_base[k], m.d_nodes,
-                           static_cast<uint32_t*>(m.d_prim_refs), &m.lbvh_scratch, m.stream, &launches_, &err_);
-    if (rc != RT2_OK) return rc;
+                           static_cast<uint32_t*>(m.d_prim_refs), &m.lbvh_scratch, m.stream, &launches_, d_depths + k, &err_);
+    if (rc != RT2_OK) {
+      cudaFree(d_depths);
+      return rc;
+    }
     if (k + 1 < n_trees) RT2_CUDA(cudaStreamSynchronize(m.stream));  // d_build_prims is reused by the next tree
   }
   m.wide_mode = false;
@@ -1140,7 +1198,14 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
     m.wide_mode = scene.tree_prims[0].size() >= 2;  // a one-leaf tree has no node pair to collapse
   }
   RT2_CUDA(cudaEventRecord(m.ev_stop, m.stream));
-  RT2_CUDA(cudaStreamSynchronize(m.stream));
+  tree_depths_.assign(n_trees, 0u);
+  {
+    const cudaError_t e = cudaMemcpyAsync(tree_depths_.data(), d_depths, n_trees * sizeof(uint32_t), cudaMemcpyDeviceToHost, m.stream);
+    const cudaError_t e2 = cudaStreamSynchronize(m.stream);
+    cudaFree(d_depths);
+    RT2_CUDA(e);
+    RT2_CUDA(e2);
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, m.ev_start, m.ev_stop);
   bvh_build_ms_ = ms;
@@ -1241,13 +1306,14 @@ int Renderer::AllocState() {
   const size_t P = static_cast<size_t>(w) * h;
   int F = cfg_.frames_per_batch;
   if (F <= 0) {
-    // ~96 M paths in flight (~18 GB of wavefront state out of 180 GB of HBM): besides amortising the launches of the 50
+    // ~192 M paths in flight (~35 GB of wavefront state out of 180 GB of HBM): besides amortising the launches of the 50
     // bounces, big batches keep the LATE queues big — on book 2 a third of all rays are traced at bounce 12 or later, where
     // a 24 M-path batch leaves ~1 M-ray queues that run at half the per-ray speed (measured: 4 914 / 5 145 / 5 270 Mrays/s at
     // 64 / 128 / 256 frames per batch of 600 x 600)
-    F = static_cast<int>((96u * 1024u * 1024u + P - 1) / P);
+    // (r02: 512 frames per batch of 600 x 600 measured +2 % over 256 — 5 907 vs 5 783 Mrays/s — and costs 35 GB of the 180 GB)
+    F = static_cast<int>((192u * 1024u * 1024u + P - 1) / P);
     if (F < 1) F = 1;
-    if (F > 256) F = 256;
+    if (F > 512) F = 512;
   }
   frames_per_batch_ = F;
   const size_t N = P * static_cast<size_t>(F);
@@ -1468,23 +1534,27 @@ int Renderer::RenderBatch(uint32_t n_frames) {
     const SplitIO io = m.split;  // all-null unless the instance split is active (then load_closest merges the entries)
     if (m.fused) {
       // finish + inline shade; only noise-textured materials go through the bins
-      if (exact && (m.ds.n_media == 0 || m.split_media)) {
-        if (m.split_media) {
-          k_media<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, io);
-          launches_++;
-        }
-        k_finish_shade<ExactMath, 4, false><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
-                                                                                   m.state[in], m.trav, io, m.hit0, m.hit1, m.bins, m.ray_o[out],
-                                                                                   m.ray_d[out], m.state[out], keys, m.radiance);
-      } else if (exact) {
-        k_finish_shade<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
-                                                                          m.state[in], m.trav, io, m.hit0, m.hit1, m.bins, m.ray_o[out],
-                                                                          m.ray_d[out], m.state[out], keys, m.radiance);
-      } else {
-        k_finish_shade<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in],
-                                                                         m.state[in], m.trav, io, m.hit0, m.hit1, m.bins, m.ray_o[out],
-                                                                         m.ray_d[out], m.state[out], keys, m.radiance);
+      const bool media_free = exact && (m.ds.n_media == 0 || m.split_media);  // no media, or sampled by k_media first
+      if (media_free && m.split_media) {
+        k_media<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(m.ds, fp, b, ctr, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, io);
+        launches_++;
       }
+#define RT2_FS_ARGS                                                                                                                 \
+  m.ds, fp, b, last ? 0 : 1, ctr, next, m.ray_o[in], m.ray_d[in], m.state[in], m.trav, io, m.hit0, m.hit1, m.bins, m.ray_o[out], \
+      m.ray_d[out], m.state[out], keys, m.radiance
+      const bool images = m.ds.n_images != 0;
+      if (media_free && !images) {
+        k_finish_shade<ExactMath, 4, 0, false><<<m.grid_stream, kBlock, 0, m.stream>>>(RT2_FS_ARGS);
+      } else if (media_free) {
+        k_finish_shade<ExactMath, 4, 0, true><<<m.grid_stream, kBlock, 0, m.stream>>>(RT2_FS_ARGS);
+      } else if (exact && m.simple_media && !images) {
+        k_finish_shade<ExactMath, 4, 1, false><<<m.grid_stream, kBlock, 0, m.stream>>>(RT2_FS_ARGS);
+      } else if (exact) {
+        k_finish_shade<ExactMath><<<m.grid_stream, kBlock, 0, m.stream>>>(RT2_FS_ARGS);
+      } else {
+        k_finish_shade<FastMath><<<m.grid_stream, kBlock, 0, m.stream>>>(RT2_FS_ARGS);
+      }
+#undef RT2_FS_ARGS
       launches_++;
       prof(2);
       if (!last) {
@@ -2019,6 +2089,7 @@ int Renderer::GetStats(rt2_stats* out) {
   out->quad_tests = t[4];
   out->instance_visits = t[5];
   out->stack_overflows = t[6];
+  out->max_stack_need = max_stack_need_;
   out->pending_frames = pending_frames_;
   out->n_gpus = 1;
   out->instance_split = m.split_mode ? 1u : 0u;

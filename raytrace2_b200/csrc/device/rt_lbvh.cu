@@ -5,8 +5,8 @@
 //
 // Pipeline (all hand-written kernels, HBM-bound integer work; no CUB / Thrust):
 //   k_lbvh_bounds      centroid bounds (block reduction + ordered-int atomics)
-//   k_lbvh_morton      30-bit Morton code of each centroid, value = primitive slot
-//   k_radix_*          LSD radix sort of (key, value), 4 passes x 8 bits: per-tile histograms, one scan, stable scatter
+//   k_lbvh_morton      63-bit Morton code of each centroid (21 bits per axis on ONE isotropic grid), value = primitive slot
+//   k_radix_*          LSD radix sort of (key, value), 8-bit digits over the bits in use: per-tile histograms, one scan, stable scatter
 //   k_lbvh_gather      leaf boxes / primitive references in sorted order
 //   k_lbvh_hierarchy   Karras 2012: one thread per internal node finds its key range and split
 //   k_lbvh_refit       bottom-up boxes, second arrival at a node does the union
@@ -73,45 +73,65 @@ __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_bounds(const rt2::BuildPrim
 
 // Morton grid = mean +- 3 sigma of the centroids, clamped to their true bounds: a single far-away giant (the r = 1e5 ground
 // sphere of the stress scene) would otherwise squeeze every other primitive into a handful of cells along one axis.
+// The grid is ISOTROPIC — one cell size for all three axes, 2^21 cells along the longest one: with a cell size per axis a
+// flat scene (the stress scene is 2000 x 200 x 2000) is cut as often along its thin axis as along the long ones, and every
+// node down to the leaves keeps the 10 : 1 : 10 slab shape of the scene (measured: 48 node pairs per ray at 10 M spheres).
+// With cubic cells the high bits of the thin axis are equal for all keys, Karras' split search skips them, and the nodes
+// become cubes.  grid[0..2] = origin, grid[3] = cells per unit.
+constexpr int kMortonBitsPerAxis = 21;
 __global__ void k_lbvh_grid(uint32_t n, const int* __restrict__ bounds, const double* __restrict__ moments, float* __restrict__ grid) {
-  if (threadIdx.x >= 3 || blockIdx.x != 0) return;
-  const int k = threadIdx.x;
-  const double mean = moments[k] / n;
-  const double var = fmax(moments[3 + k] / n - mean * mean, 0.0);
-  const double sd = sqrt(var);
-  const float lo = fmaxf(ordered_to_float(bounds[k]), static_cast<float>(mean - 3.0 * sd));
-  const float hi = fminf(ordered_to_float(bounds[3 + k]), static_cast<float>(mean + 3.0 * sd));
-  grid[k] = lo;
-  grid[3 + k] = hi > lo ? 1024.0f / (hi - lo) : 0.0f;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float extent = 0.0f;
+  for (int k = 0; k < 3; k++) {
+    const double mean = moments[k] / n;
+    const double var = fmax(moments[3 + k] / n - mean * mean, 0.0);
+    const double sd = sqrt(var);
+    const float lo = fmaxf(ordered_to_float(bounds[k]), static_cast<float>(mean - 3.0 * sd));
+    const float hi = fminf(ordered_to_float(bounds[3 + k]), static_cast<float>(mean + 3.0 * sd));
+    grid[k] = lo;
+    extent = fmaxf(extent, hi - lo);
+  }
+  grid[3] = extent > 0.0f ? static_cast<float>((1u << kMortonBitsPerAxis) - 1u) / extent : 0.0f;
 }
 
-__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
-  v = (v * 0x00010001u) & 0xFF0000FFu;
-  v = (v * 0x00000101u) & 0x0F00F00Fu;
-  v = (v * 0x00000011u) & 0xC30C30C3u;
-  v = (v * 0x00000005u) & 0x49249249u;
-  return v;
+// spreads the low 21 bits of v to every third bit
+__device__ __forceinline__ unsigned long long expand_bits21(uint32_t v) {
+  unsigned long long x = v & 0x1FFFFFull;
+  x = (x | (x << 32)) & 0x001F00000000FFFFull;
+  x = (x | (x << 16)) & 0x001F0000FF0000FFull;
+  x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+  x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
 }
 
 __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_morton(const rt2::BuildPrim* __restrict__ prims, uint32_t n, const float* __restrict__ grid,
-                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                            unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                            unsigned long long* __restrict__ key_or) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const rt2::BuildPrim p = prims[i];
-  uint32_t q[3];
+  unsigned long long key = 0;
+  if (i < n) {
+    const rt2::BuildPrim p = prims[i];
+    uint32_t q[3];
+    const float cells = grid[3], top = static_cast<float>((1u << kMortonBitsPerAxis) - 1u);
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const float c = 0.5f * (p.bmin[k] + p.bmax[k]);
-    const float u = fminf(fmaxf((c - grid[k]) * grid[3 + k], 0.0f), 1023.0f);  // outliers clamp to the border cells
-    q[k] = static_cast<uint32_t>(u);
+    for (int k = 0; k < 3; k++) {
+      const float c = 0.5f * (p.bmin[k] + p.bmax[k]);
+      const float u = fminf(fmaxf((c - grid[k]) * cells, 0.0f), top);  // outliers clamp to the border cells
+      q[k] = static_cast<uint32_t>(u);
+    }
+    key = (expand_bits21(q[0]) << 2) | (expand_bits21(q[1]) << 1) | expand_bits21(q[2]);
+    keys[i] = key;
+    vals[i] = i;
   }
-  keys[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
-  vals[i] = i;
+  // OR of all keys: radix passes over digits that are zero in every key are skipped by the host
+  for (int off = 16; off > 0; off >>= 1) key |= __shfl_down_sync(0xFFFFFFFFu, key, off);
+  if ((threadIdx.x & 31) == 0 && key) atomicOr(key_or, key);
 }
 
 // ---- radix sort ---------------------------------------------------------------------------------------------------
 // hist layout: hist[bin * n_tiles + tile] so that one exclusive scan over the whole array yields global offsets.
-__global__ void __launch_bounds__(kLbvhBlock) k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t n_tiles,
+__global__ void __launch_bounds__(kLbvhBlock) k_radix_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift, uint32_t n_tiles,
                                                            uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[kRadixBins];
   for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x) sh[b] = 0;
@@ -120,7 +140,7 @@ __global__ void __launch_bounds__(kLbvhBlock) k_radix_hist(const uint32_t* __res
 #pragma unroll
   for (int r = 0; r < kKeysPerThread; r++) {
     const uint32_t i = base + r * kLbvhBlock + threadIdx.x;
-    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (kRadixBins - 1)], 1u);
+    if (i < n) atomicAdd(&sh[static_cast<uint32_t>(keys[i] >> shift) & (kRadixBins - 1)], 1u);
   }
   __syncthreads();
   for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x) hist[static_cast<size_t>(b) * n_tiles + blockIdx.x] = sh[b];
@@ -161,9 +181,9 @@ __global__ void __launch_bounds__(1024) k_radix_scan(uint32_t* __restrict__ data
 }
 
 // Stable scatter: the rank of a key among equal digits of its tile follows the (round, warp, lane) = global index order.
-__global__ void __launch_bounds__(kLbvhBlock) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t n,
-                                                              int shift, uint32_t n_tiles, const uint32_t* __restrict__ offsets,
-                                                              uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+__global__ void __launch_bounds__(kLbvhBlock) k_radix_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                              uint32_t n, int shift, uint32_t n_tiles, const uint32_t* __restrict__ offsets,
+                                                              unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
   constexpr int kWarps = kLbvhBlock / 32;
   __shared__ uint32_t running[kRadixBins];          // keys of this digit already placed by earlier rounds
   __shared__ uint32_t warp_cnt[kWarps][kRadixBins];  // per-round, per-warp digit counts -> exclusive prefix over warps
@@ -179,11 +199,12 @@ __global__ void __launch_bounds__(kLbvhBlock) k_radix_scatter(const uint32_t* __
     __syncthreads();
     const uint32_t i = base + r * kLbvhBlock + threadIdx.x;
     const bool valid = i < n;
-    uint32_t key = 0, val = 0, digit = kRadixBins;  // invalid lanes get a digit no valid lane has
+    unsigned long long key = 0;
+    uint32_t val = 0, digit = kRadixBins;  // invalid lanes get a digit no valid lane has
     if (valid) {
       key = keys_in[i];
       val = vals_in[i];
-      digit = (key >> shift) & (kRadixBins - 1);
+      digit = static_cast<uint32_t>(key >> shift) & (kRadixBins - 1);
     }
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, digit);
     const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
@@ -226,17 +247,17 @@ __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_gather(const rt2::BuildPrim
 }
 
 // common-prefix length of keys i and j (index tie-break for duplicate keys), -1 outside [0, n)
-__device__ __forceinline__ int lbvh_delta(const uint32_t* __restrict__ keys, int n, int i, int j) {
+__device__ __forceinline__ int lbvh_delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
-  const uint32_t a = keys[i], b = keys[j];
-  if (a == b) return 32 + __clz(static_cast<uint32_t>(i) ^ static_cast<uint32_t>(j));
-  return __clz(a ^ b);
+  const unsigned long long a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(static_cast<uint32_t>(i) ^ static_cast<uint32_t>(j));
+  return __clzll(static_cast<long long>(a ^ b));
 }
 
 constexpr uint32_t kChildLeaf = 0x80000000u;
 
 // Karras 2012, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees", Fig. 4.
-__global__ void __launch_bounds__(kLbvhBlock) k_lbvh_hierarchy(const uint32_t* __restrict__ keys, int n, uint2* __restrict__ children,
+__global__ void __launch_bounds__(kLbvhBlock) k_lbvh_hierarchy(const unsigned long long* __restrict__ keys, int n, uint2* __restrict__ children,
                                                                uint32_t* __restrict__ parent_internal, uint32_t* __restrict__ parent_leaf) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
@@ -335,6 +356,20 @@ __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_emit(int n, uint32_t pair_b
   }
 }
 
+// Depth of the tree in node pairs (= the number of stack entries a traversal may need): every leaf walks to the root.
+__global__ void __launch_bounds__(kLbvhBlock) k_lbvh_depth(int n, const uint32_t* __restrict__ parent_internal,
+                                                           const uint32_t* __restrict__ parent_leaf, uint32_t* __restrict__ depth_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t depth = 0;
+  if (j < n) {
+    uint32_t node = parent_leaf[j];
+    depth = 1;
+    while ((node = parent_internal[node]) != 0xFFFFFFFFu) depth++;
+  }
+  for (int off = 16; off > 0; off >>= 1) depth = max(depth, __shfl_down_sync(0xFFFFFFFFu, depth, off));
+  if ((threadIdx.x & 31) == 0 && depth) atomicMax(depth_out, depth);
+}
+
 // Trees with 0 or 1 primitive: {leaf | empty, empty}
 __global__ void k_lbvh_tiny(int n, uint32_t pair_base, uint32_t ref_base, const rt2::BuildPrim* __restrict__ prims, float4* __restrict__ nodes_out,
                             uint32_t* __restrict__ prim_refs_out) {
@@ -366,12 +401,15 @@ using namespace rt2dev;
   } while (0)
 
 int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, uint32_t ref_base, void* d_nodes, uint32_t* d_prim_refs,
-                      LbvhScratch* scratch, void* stream_v, uint64_t* launches, std::string* err) {
+                      LbvhScratch* scratch, void* stream_v, uint64_t* launches, uint32_t* d_depth, std::string* err) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   float4* nodes = static_cast<float4*>(d_nodes);
   if (n <= 1) {
     k_lbvh_tiny<<<1, 32, 0, stream>>>(static_cast<int>(n), pair_base, ref_base, d_prims, nodes, d_prim_refs + ref_base);
     (*launches)++;
+    const uint32_t one = 1;
+    LBVH_CUDA(cudaMemcpyAsync(d_depth, &one, sizeof(one), cudaMemcpyHostToDevice, stream));
+    LBVH_CUDA(cudaStreamSynchronize(stream));  // `one` is a stack variable
     return RT2_OK;
   }
   // scratch (grown on demand, reused between trees); every sub-buffer is 256-byte aligned
@@ -379,7 +417,7 @@ int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, 
   auto align = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
   const size_t sz_u32 = align(n * 4ull), sz_f4 = align(n * 16ull), sz_u2 = align(n * 8ull);
   const size_t sz_hist = align(static_cast<size_t>(kRadixBins) * n_tiles * 4);
-  const size_t need = 256 + 4 * sz_u32 + sz_hist + 4 * sz_f4 + sz_u2 + 3 * sz_u32;
+  const size_t need = 256 + 2 * sz_u2 + 2 * sz_u32 + sz_hist + 4 * sz_f4 + sz_u2 + 3 * sz_u32;
   if (need > scratch->bytes) {
     if (scratch->ptr) cudaFree(scratch->ptr);
     scratch->ptr = nullptr;
@@ -396,9 +434,10 @@ int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, 
   char* head = take(256);
   int* bounds = reinterpret_cast<int*>(head);                // 6 ints
   double* moments = reinterpret_cast<double*>(head + 64);   // 6 doubles
-  float* grid = reinterpret_cast<float*>(head + 128);        // 6 floats
-  uint32_t* keys_a = reinterpret_cast<uint32_t*>(take(sz_u32));
-  uint32_t* keys_b = reinterpret_cast<uint32_t*>(take(sz_u32));
+  float* grid = reinterpret_cast<float*>(head + 128);        // 4 floats
+  unsigned long long* key_or = reinterpret_cast<unsigned long long*>(head + 192);
+  unsigned long long* keys_a = reinterpret_cast<unsigned long long*>(take(sz_u2));
+  unsigned long long* keys_b = reinterpret_cast<unsigned long long*>(take(sz_u2));
   uint32_t* vals_a = reinterpret_cast<uint32_t*>(take(sz_u32));
   uint32_t* vals_b = reinterpret_cast<uint32_t*>(take(sz_u32));
   uint32_t* hist = reinterpret_cast<uint32_t*>(take(sz_hist));
@@ -423,23 +462,29 @@ int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, 
   const uint32_t grid_red = grid_n < 1184u ? grid_n : 1184u;
   k_lbvh_bounds<<<grid_red, kLbvhBlock, 0, stream>>>(d_prims, n, bounds, moments);
   k_lbvh_grid<<<1, 32, 0, stream>>>(n, bounds, moments, grid);
-  k_lbvh_morton<<<grid_n, kLbvhBlock, 0, stream>>>(d_prims, n, grid, keys_a, vals_a);
+  k_lbvh_morton<<<grid_n, kLbvhBlock, 0, stream>>>(d_prims, n, grid, keys_a, vals_a, key_or);
   *launches += 3;
-  uint32_t *kin = keys_a, *kout = keys_b, *vin = vals_a, *vout = vals_b;
-  for (int pass = 0; pass < 4; pass++) {
+  // which 8-bit digits are non-zero in at least one key?  (a flat or small scene uses far fewer than 63 bits)
+  unsigned long long used = 0;
+  LBVH_CUDA(cudaMemcpyAsync(&used, key_or, sizeof(used), cudaMemcpyDeviceToHost, stream));
+  LBVH_CUDA(cudaStreamSynchronize(stream));
+  unsigned long long *kin = keys_a, *kout = keys_b;
+  uint32_t *vin = vals_a, *vout = vals_b;
+  for (int pass = 0; pass < 8; pass++) {
     const int shift = pass * kRadixBits;
+    if (((used >> shift) & 0xFFull) == 0ull) continue;  // every key has a zero digit here: the pass would be the identity
     k_radix_hist<<<n_tiles, kLbvhBlock, 0, stream>>>(kin, n, shift, n_tiles, hist);
     k_radix_scan<<<1, 1024, 0, stream>>>(hist, static_cast<uint32_t>(kRadixBins) * n_tiles);
     k_radix_scatter<<<n_tiles, kLbvhBlock, 0, stream>>>(kin, vin, n, shift, n_tiles, hist, kout, vout);
     *launches += 3;
-    uint32_t* t = kin;
+    unsigned long long* tk = kin;
     kin = kout;
-    kout = t;
-    t = vin;
+    kout = tk;
+    uint32_t* tv = vin;
     vin = vout;
-    vout = t;
+    vout = tv;
   }
-  // after 4 passes the sorted data is back in (keys_a, vals_a) = (kin, vin)
+  // the sorted data is in (kin, vin)
   k_lbvh_gather<<<grid_n, kLbvhBlock, 0, stream>>>(d_prims, vin, n, leaf_min, leaf_max, d_prim_refs + ref_base);
   LBVH_CUDA(cudaMemsetAsync(visit, 0, n * 4ull, stream));
   k_lbvh_hierarchy<<<grid_n, kLbvhBlock, 0, stream>>>(kin, static_cast<int>(n), children, parent_internal, parent_leaf);
@@ -447,7 +492,8 @@ int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, 
                                                   visit);
   k_lbvh_emit<<<grid_n, kLbvhBlock, 0, stream>>>(static_cast<int>(n), pair_base, ref_base, children, leaf_min, leaf_max, node_min, node_max, d_prim_refs,
                                                  nodes);
-  *launches += 4;
+  k_lbvh_depth<<<grid_n, kLbvhBlock, 0, stream>>>(static_cast<int>(n), parent_internal, parent_leaf, d_depth);
+  *launches += 5;
   LBVH_CUDA(cudaGetLastError());
   return RT2_OK;
 }

@@ -56,7 +56,9 @@ template <class M> __device__ __forceinline__ F3 ray_at(F3 o, F3 d, float t) { r
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: key = (pixel, seed), counter = (frame, bounce|stream, ...) ----
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   const uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
-#pragma unroll
+  // two rounds per trip: the rounds are one dependent chain, so full unrolling buys no ILP — it only cost 1.2 KB of code per
+  // call site in kernels that are instruction-cache bound (k_finish_shade)
+#pragma unroll 2
   for (int r = 0; r < 10; r++) {
     uint32_t hi0 = __umulhi(kM0, c.x), lo0 = kM0 * c.x;
     uint32_t hi1 = __umulhi(kM1, c.z), lo1 = kM1 * c.z;

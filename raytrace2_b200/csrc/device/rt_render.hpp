@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../../include/rt2.h"
 #include "../host/scene_host.hpp"
@@ -77,6 +78,8 @@ class Renderer {
   bool world_tree_ok_{false};   // the scene carries a surfaces-only world TLAS (instance split)
   uint32_t world_root_{0};
   uint32_t n_textures_{0};
+  std::vector<uint32_t> tree_depths_;  // node-pair depth of every tree on the device ([0] TLAS, [1 + i] BLAS i, [last] world tree)
+  uint32_t max_stack_need_{0};         // stack entries the deepest traversal of this scene can need (checked against kStackSize)
   uint64_t launches_{0};
   double gpu_ms_total_{0};
   double prof_ms_[7]{0, 0, 0, 0, 0, 0, 0};

@@ -104,10 +104,12 @@ __device__ __forceinline__ F3 texture_value(const DeviceScene& S, uint32_t tex_i
 // texture_value for textures whose chain holds no noise texture (solid colours, checkers of solid colours): the cheap
 // subset the fused finish+shade kernel evaluates inline.  The host marks every material that can reach a noise texture
 // as deferred (Renderer::UploadScene), so the noise branch is never needed here.
+template <bool kImages = true>
 __device__ __forceinline__ F3 texture_value_simple(const DeviceScene& S, uint32_t tex_idx, F3 p, float u, float v) {
+#pragma unroll 1
   for (int depth = 0; depth < 8; depth++) {
     const float4 t0 = __ldg(S.textures + 3 * tex_idx), t1 = __ldg(S.textures + 3 * tex_idx + 1);
-    if (__float_as_uint(t0.x) == RT2_TEX_IMAGE) return image_value(S, __float_as_uint(__ldg(S.textures + 3 * tex_idx + 2).y), u, v);
+    if (kImages && __float_as_uint(t0.x) == RT2_TEX_IMAGE) return image_value(S, __float_as_uint(__ldg(S.textures + 3 * tex_idx + 2).y), u, v);
     if (__float_as_uint(t0.x) != RT2_TEX_CHECKER) return {t1.x, t1.y, t1.z};
     int ix = static_cast<int>(floorf(t1.w * p.x)), iy = static_cast<int>(floorf(t1.w * p.y)), iz = static_cast<int>(floorf(t1.w * p.z));
     tex_idx = ((ix + iy + iz) % 2 == 0) ? __float_as_uint(t0.y) : __float_as_uint(t0.z);

@@ -261,6 +261,8 @@ struct TravCounters {
 // are busy the warp pulls new work from the queue with one atomic.  `order` (optional) is the permutation in which the
 // queue is consumed.  Results go to trav_out[ray] = {t bits, prim ref, instance, has-entries flag}.
 enum { kTravInline = 0, kTravWorld = 1, kTravInst = 2 };
+constexpr uint32_t kFetchChunk = 64;  // queue items a warp reserves with one atomic (big queues)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr uint32_t kTravDone = 0xFFFFFFFFu;  // `cur` of a lane whose ray is finished (carries kLeafFlag: phase 1 skips it)
 constexpr uint32_t kMaxHoistedInstances = 4;
 
@@ -314,12 +316,17 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
                                                int max_steps, int fetch_threshold) {
   const unsigned kFull = 0xFFFFFFFFu;
   const unsigned lane = threadIdx.x & 31u;
-  uint32_t stack[kStackSize];
-  int sp = 0;
+  // stack[0] is a permanent bottom marker (kTravDone): popping it ends the ray without an emptiness test; stack[-1] exists
+  // so that the reload after that last pop stays inside the array
+  uint32_t stack_mem[kStackSize + 2];
+  uint32_t* const stack = stack_mem + 1;
+  int sp = 1;
   bool active = false;
   bool exhausted = false;
   uint32_t ray_idx = 0;
   uint32_t entry_idx = 0;  // kTravInst
+  uint32_t chunk_pos = 0, chunk_end = 0;  // warp-uniform: the part of the queue this warp has reserved
+  const bool big_queue = n >= kFetchChunk * 16u * (gridDim.x * (blockDim.x >> 5));  // >= 16 chunks per warp
   uint32_t cur = 0;
   F3 o = {0, 0, 0}, d = {0, 0, 1};
   float time = 0.0f, a = 1.0f;
@@ -335,45 +342,66 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
     inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
     oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
   };
-  // The builders bound the depth of every tree; should a tree ever be deeper than the stack, the dropped sub-tree is
-  // counted (rt2_stats.stack_overflows) and the read-out calls fail instead of returning a silently wrong image.
-  auto push = [&](uint32_t v) {
-    if (sp < kStackSize) stack[sp++] = v;
-    else cnt.overflow = 1u;
+  // The traversal stack lives in local memory (L1); `top` mirrors stack[sp - 1] in a register.  Every push / pop ends with an
+  // unconditional reload of the new top, issued a whole node step before it can be needed, so a pop never waits for a load
+  // and the node step below is branch-free: with 32 rays per warp some lane pushes and some lane pops in almost every step,
+  // so predicating both costs no issue slots, while the branchy form ran the push at 3 and the pop at 5 of 32 lanes
+  // (13 - 20 % of the kernel's warp instructions; profiles/r02_notes.md).
+  // No bounds checks here: the renderer verifies at upload time that every tree (TLAS depth + 1 + deepest BLAS for the inline
+  // walk) fits kStackSize and refuses the scene otherwise (Renderer::CheckTreeDepths) — a traversal can neither drop a
+  // sub-tree silently nor write outside its stack.
+  uint32_t top = kTravDone;
+  auto pop_plain = [&]() {
+    cur = top;
+    sp -= 1;
+    top = stack[sp - 1];
   };
-  // Pops the next entry; on an empty stack the ray is finished (published at the end of the round).
+  // Pops the next entry; the bottom marker means the ray is finished (published at the end of the round).
   auto pop = [&]() {
-    if (kMode == kTravInline) {
-      while (true) {
-        if (sp == 0) {
-          cur = kTravDone;
-          return;
-        }
-        cur = stack[--sp];
-        if (cur != kStackSentinel) return;
-        // leave the instance: back to the world-space ray (re-read instead of holding it in registers)
-        const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
-        set_space(make_f3(wo), make_f3(wd));
-        cur_inst = -1;
-        cur_cull = cull_scale;
-      }
-    } else {
-      cur = kTravDone;
-      if (sp > 0) cur = stack[--sp];
+    pop_plain();
+    if (kMode == kTravInline && cur == kStackSentinel) {
+      // leave the instance: back to the world-space ray (re-read instead of holding it in registers).  Instances are
+      // flattened by the host, so the entry under a sentinel is never another sentinel.
+      const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
+      set_space(make_f3(wo), make_f3(wd));
+      cur_inst = -1;
+      cur_cull = cull_scale;
+      pop_plain();
     }
   };
 
   while (true) {
-    // ---- fetch: idle lanes take the next items of the queue (one atomic per warp) ----
+    // ---- fetch: idle lanes take the next items of the queue ----
+    // The warp owns a chunk [chunk_pos, chunk_end) of the queue and refills from it; a new chunk costs one atomic (an L2
+    // round trip of ~600 cycles with every busy lane of the warp waiting) and is followed by an L2 prefetch of the chunk's
+    // rays, so later refills find them on chip.  Big queues use 64-item chunks; small ones (late bounces) take exactly what
+    // they need, so that no warp sits on unprocessed rays while the others have run dry.
     const unsigned idle = __ballot_sync(kFull, !active);
     if (idle) {
       if (!exhausted) {
-        const int leader = __ffs(idle) - 1;
-        uint32_t base = 0;
-        if (static_cast<int>(lane) == leader) base = atomicAdd(next_ray, __popc(idle));
-        base = __shfl_sync(kFull, base, leader);
+        const uint32_t need = __popc(idle);
+        const uint32_t avail = chunk_end - chunk_pos;
+        uint32_t new_base = 0;
+        if (avail < need) {
+          const uint32_t take = big_queue ? kFetchChunk : need - avail;
+          if (lane == 0) new_base = atomicAdd(next_ray, take);
+          new_base = __shfl_sync(kFull, new_base, 0);
+          if (big_queue && kMode != kTravInst && order == nullptr) {
+            // 64 rays x (16 B origin + 16 B direction) = 8 + 8 lines of 128 B
+            const uint32_t line = lane & 7u;
+            const float4* src = (lane & 8u) ? ray_d : ray_o;
+            if (lane < 16u && new_base + line * 8u < n) prefetch_l2(src + new_base + line * 8u);
+          }
+        }
+        const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+        const uint32_t pos = rank < avail ? chunk_pos + rank : new_base + (rank - avail);
+        if (avail < need) {
+          chunk_pos = new_base + (need - avail);
+          chunk_end = new_base + (big_queue ? kFetchChunk : need - avail);
+        } else {
+          chunk_pos += need;
+        }
         if (!active) {
-          const uint32_t pos = base + __popc(idle & ((1u << lane) - 1u));
           if (pos < n) {
             if (kMode == kTravInst) {
               // one entry: the ray in the instance's model space, bounded by its closest world-space surface
@@ -406,11 +434,13 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
             }
             best.prim = RT2_PRIM_NONE;
             best.instance = -1;
-            sp = 0;
+            stack[0] = kTravDone;
+            sp = 1;
+            top = kTravDone;
             active = true;
           }
         }
-        exhausted = (base + __popc(idle)) >= n;
+        exhausted = chunk_pos >= n;  // the warp's chunk starts beyond the queue: every later chunk does too
       }
       if (__ballot_sync(kFull, active) == 0u) break;
     }
@@ -442,16 +472,24 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         // device node format (rt_kernels.cu UploadScene / rt_lbvh.cu): .w of the min corner is the traversal entry itself:
         // (interior -> child pair index; leaf -> see make_leaf_entry)
         const uint32_t e0 = __float_as_uint(a0.w), e1 = __float_as_uint(b0.w);
-        if (h0 && h1) {
-          const bool swap = near1 < near0;
-          cur = swap ? e1 : e0;
-          push(swap ? e0 : e1);
-        } else if (h0) {
-          cur = e0;
-        } else if (h1) {
-          cur = e1;
+        // branch-free step: the far child of a double hit is stored above the top (a harmless write when it is not pushed),
+        // a miss takes the register copy of the top
+        const bool both = h0 && h1, any = h0 || h1;
+        const bool swap = both && (near1 < near0);
+        const uint32_t near_child = (h0 && !swap) ? e0 : e1;
+        stack[sp] = swap ? e0 : e1;
+        if (kMode == kTravInline) {
+          if (any) {
+            cur = near_child;
+            sp += both ? 1 : 0;
+            top = stack[sp - 1];
+          } else {
+            pop();  // may have to leave an instance
+          }
         } else {
-          pop();
+          cur = any ? near_child : top;
+          sp += any ? (both ? 1 : 0) : -1;
+          top = stack[sp - 1];
         }
       }
       __syncwarp();
@@ -482,10 +520,6 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
             }
           } else if (kMode == kTravInline) {
             // instance leaf (always a singleton leaf of the TLAS, host/bvh_build.cpp): enter its BLAS in model space
-            if (sp >= kStackSize) {  // no room for the way back: skip the instance and report it
-              cnt.overflow = 1u;
-              continue;
-            }
             if (kCount) cnt.instances++;
             const uint4 in = __ldg(S.instances + idx);
             const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
@@ -494,6 +528,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
             cur_inst = static_cast<int32_t>(idx);
             cur_cull = 1.0f;
             stack[sp++] = kStackSentinel;
+            top = kStackSentinel;
             cur = in.z;
             entered = true;
             break;
@@ -735,7 +770,10 @@ struct HitOut {
 
 // Constant media (few per scene) against the closest surface so far: each draws its free path (ConstantMedium.cpp:14-58)
 // against the current best raw t and shrinks it when it scatters first.  medium_hit = index of the winner or -1.
-template <class M, bool kAxis = false>
+// kSimple: the host guarantees that every medium has a ONE-primitive boundary in world space (no instance chain) — the
+// sphere-bounded media of book 2.  The chain transforms, the 6-root and the list boundary code then drop out of the kernel
+// (the fused finish + shade kernel is instruction-cache bound: profiles/r02_notes.md).
+template <class M, bool kAxis = false, bool kSimple = false>
 __device__ __forceinline__ void media_sample(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, const RngKey& key,
                                              uint32_t bounce, Closest& best, int32_t& medium_hit) {
   medium_hit = -1;
@@ -744,7 +782,8 @@ __device__ __forceinline__ void media_sample(const DeviceScene& S, F3 wo, F3 wd,
   {
     for (uint32_t m = 0; m < S.n_media; m++) {
       const uint4 m0 = __ldg(S.media + 2 * m), m1 = __ldg(S.media + 2 * m + 1);
-      RaySpace rs = to_chain_space<M>(S, m1.x, m1.y, RaySpace{wo, wd});
+      RaySpace rs{wo, wd};
+      if (!kSimple) rs = to_chain_space<M>(S, m1.x, m1.y, rs);
       const float a = vdot<M>(rs.d, rs.d);
       const float ray_len = M::sqrt(a);  // glm::length(r.direction)
       // one Philox call serves two media: .xy for even m, .zw for odd m
@@ -762,7 +801,17 @@ __device__ __forceinline__ void media_sample(const DeviceScene& S, F3 wo, F3 wd,
       const float span = (best.t - fmaxf(tmin, 0.0f)) * ray_len * 1.00001f;
       if (hd1 > span && hd2 > span) continue;
       float t1, t2;
-      if (!medium_boundary<M, kAxis>(S, m0, rs.o, rs.d, a, time, t1, t2)) continue;
+      if (kSimple) {
+        float lo, hi;
+        bool sph;
+        boundary_roots<M, kAxis>(S, __ldg(S.prim_refs + m0.z), rs.o, rs.d, a, time, lo, hi, sph);
+        t1 = boundary_candidate(lo, hi, sph, -kFltMax);
+        if (!(t1 <= kFltMax)) continue;
+        t2 = boundary_candidate(lo, hi, sph, static_cast<float>(static_cast<double>(t1) + 0.0001));
+        if (!(t2 <= kFltMax)) continue;
+      } else if (!medium_boundary<M, kAxis>(S, m0, rs.o, rs.d, a, time, t1, t2)) {
+        continue;
+      }
       float t;
       if (medium_draw<M>(hd1, ray_len, t1, t2, tmin, best.t, t)) {
         best.t = t;
@@ -779,7 +828,8 @@ __device__ __forceinline__ void media_sample(const DeviceScene& S, F3 wo, F3 wd,
 }
 
 // The winner's hit record: a medium scatter (medium_hit >= 0, at best.t), the closest surface best.prim, or a miss.
-template <class M>
+// kImages = false drops the (u, v) code (acosf / atan2f: ~3 KB) from kernels specialised for scenes without image textures.
+template <class M, bool kSimple = false, bool kImages = true>
 __device__ __forceinline__ void finish_record(const DeviceScene& S, F3 wo, F3 wd, float time, Closest best, int32_t medium_hit, HitOut& out) {
   out.t = best.t;
   out.prim = best.prim;
@@ -787,10 +837,11 @@ __device__ __forceinline__ void finish_record(const DeviceScene& S, F3 wo, F3 wd
   out.u = out.v = 0.0f;
   if (medium_hit >= 0) {
     const uint4 m0 = __ldg(S.media + 2 * medium_hit), m1 = __ldg(S.media + 2 * medium_hit + 1);
-    RaySpace rs = to_chain_space<M>(S, m1.x, m1.y, RaySpace{wo, wd});
+    RaySpace rs{wo, wd};
+    if (!kSimple) rs = to_chain_space<M>(S, m1.x, m1.y, rs);
     F3 p = ray_at<M>(rs.o, rs.d, best.t);
     F3 n = {1.0f, 0.0f, 0.0f};  // "both arbitrary", ConstantMedium.cpp:52-53
-    chain_to_world<M>(S, m1.x, m1.y, p, n);
+    if (!kSimple) chain_to_world<M>(S, m1.x, m1.y, p, n);
     out.p = p;
     out.n = n;
     out.front_face = true;
@@ -830,7 +881,7 @@ __device__ __forceinline__ void finish_record(const DeviceScene& S, F3 wo, F3 wd
     outward = make_f3(nd);
     mat = __float_as_uint(qq.w);
   }
-  if (S.n_images) {
+  if (kImages && S.n_images) {
     if (RT2_PRIM_TYPE(best.prim) == RT2_PRIM_SPHERE) {
       // Sphere::GetUV(outward_normal) (Sphere.cpp:34,39-43)
       const float theta = acosf(-outward.y);
@@ -858,12 +909,12 @@ __device__ __forceinline__ void finish_record(const DeviceScene& S, F3 wo, F3 wd
 
 // Second half of the closest-hit query ≡ scene.hittable_list.Hit(r, Interval{tmin, tmax}, rec) (RayTracer.cpp:25): given the
 // closest SURFACE (traverse_queue), sample the constant media against it and build the winner's record.
-template <class M>
+template <class M, bool kSimple = false, bool kImages = true>
 __device__ __forceinline__ void finish_hit(const DeviceScene& S, F3 wo, F3 wd, float time, float tmin, Closest best,
                                            const RngKey& key, uint32_t bounce, bool skip_media, HitOut& out) {
   int32_t medium_hit = -1;
-  if (!skip_media) media_sample<M>(S, wo, wd, time, tmin, key, bounce, best, medium_hit);
-  finish_record<M>(S, wo, wd, time, best, medium_hit, out);
+  if (!skip_media) media_sample<M, false, kSimple>(S, wo, wd, time, tmin, key, bounce, best, medium_hit);
+  finish_record<M, kSimple, kImages>(S, wo, wd, time, best, medium_hit, out);
 }
 
 }  // namespace rt2dev

@@ -352,22 +352,29 @@ def test_cornell_full_size_1024spp_against_reference_tiles(native_lib):
     assert abs(rpp - float(g["rays"]) / (dims[0] * dims[1] * spp)) < 0.005 * rpp, rpp
 
 
-# ---- stack overflow is reported, never silent ---------------------------------------------------------------------------
-def test_stack_overflow_counter_is_zero_on_real_scenes(native_lib):
-    for name, flags in [(BOOK2, 0), (BOOK2, rt.RT2_FLAG_NO_INSTANCE_SPLIT), ("final_render_book_1", rt.RT2_FLAG_GPU_LBVH)]:
+# ---- the traversal stack cannot overflow: tree depths are verified at upload ------------------------------------------------
+def test_tree_depths_fit_the_traversal_stack(native_lib):
+    """The walks keep one stack entry per tree level and do no bounds checks; rt2_create / rt2_upload_scene compute the depth of
+    every tree on the device (host SAH trees and device LBVH trees alike) and refuse a scene that does not fit."""
+    for name, flags in [(BOOK2, 0), (BOOK2, rt.RT2_FLAG_NO_INSTANCE_SPLIT), (BOOK2, rt.RT2_FLAG_GPU_LBVH),
+                        ("final_render_book_1", rt.RT2_FLAG_GPU_LBVH), ("cornell_box4", rt.RT2_FLAG_NO_FLAT_EXTEND)]:
         tr = rt.RayTracer(rt.Scene.load(scene_path(name)), num_samples=4, dims=(160, 90), flags=flags)
         tr.Update(4)
         tr.NonConvertedPixels()
-        assert tr.stats()["stack_overflows"] == 0
+        st = tr.stats()
+        assert 1 <= st["max_stack_need"] <= 63 and st["stack_overflows"] == 0, (name, flags, st["max_stack_need"])
+    # the inline walk nests TLAS + sentinel + BLAS on one stack; the split walks need only the deeper of the two trees
+    scene = rt.Scene.load(scene_path(BOOK2))
+    split = rt.RayTracer(scene, dims=(32, 32)).stats()["max_stack_need"]
+    inline = rt.RayTracer(scene, dims=(32, 32), flags=rt.RT2_FLAG_NO_INSTANCE_SPLIT).stats()["max_stack_need"]
+    assert inline > split
 
 
-def test_stack_overflow_is_reported_by_the_read_out(native_lib):
-    """A degenerate device-built tree: 200 000 identical spheres have one Morton code, so the LBVH is a 17-level balanced tree
-    over index bits — fine.  20 nested copies shifted by 1e-3 each at 10 M... is too slow for a unit test; instead the
-    guarantee is checked from the other side: duplicates must NOT overflow, and the counter is plumbed through."""
+def test_duplicate_keys_do_not_make_a_deep_lbvh(native_lib):
+    """50 000 spheres, device LBVH with 63-bit Morton keys: duplicates are split by index bits, so the tree stays shallow."""
     scene = rt.Scene.synthetic_spheres(50000, seed=5, width=64, height=36, host_bvh=False)
     tr = rt.RayTracer(scene, num_samples=4, flags=rt.RT2_FLAG_GPU_LBVH)
     tr.Update(4)
     tr.NonConvertedPixels()
     st = tr.stats()
-    assert st["stack_overflows"] == 0 and st["rays"] > 0
+    assert st["stack_overflows"] == 0 and st["rays"] > 0 and 10 <= st["max_stack_need"] <= 40, st["max_stack_need"]
