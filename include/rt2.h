@@ -186,6 +186,13 @@ typedef struct rt2_scene_desc {
   uint32_t n_image_texels;   /* float4 texels over all images */
   const rt2_image* images;
   const float* image_texels; /* 4 * n_image_texels floats */
+  /* unified world tree: the world surfaces + every instanced primitive as a world-space leaf (leaf reference
+   * RT2_PRIM_INSTANCE << 28 | k names inst_leaves[k] = {primitive reference, instance index}) */
+  uint32_t has_unified_tlas;
+  uint32_t tlas_unified_root;
+  uint32_t n_inst_leaves;
+  uint32_t pad_unified;
+  const uint32_t* inst_leaves; /* 2 * n_inst_leaves */
   /* instance split (RT2_MAX_HOISTED_INSTANCES): a second world tree over the surfaces only, and the world boxes of the instances */
   uint32_t has_world_tlas;   /* 1 iff tlas_world_root is valid (the scene has 1..RT2_MAX_HOISTED_INSTANCES instances) */
   uint32_t tlas_world_root;  /* node-pair index */
@@ -236,8 +243,13 @@ typedef struct rt2_renderer rt2_renderer;
                                    (device radix sort); changes the traversal ORDER only, never a result.  Measured as a net
                                    loss: compiled only into `make EXPERIMENTS=1` builds, RT2_ERR_UNSUPPORTED otherwise */
 #define RT2_FLAG_NO_FLAT_EXTEND 128u /* walk the BVH even in tiny scenes that would take the tree-less flat extend kernel (A/B) */
-#define RT2_FLAG_NO_INSTANCE_SPLIT 64u /* walk instances inline (one kernel, instance leaves in the TLAS) even when the scene
-                                   qualifies for the two-pass instance split (RT2_MAX_HOISTED_INSTANCES); A/B and debugging */
+/* How instances are walked.  Default: ONE world-space tree whose leaves are the world surfaces and every primitive of every
+ * instance (each still tested in its instance's model space) — scenes whose instances hold <= 4 M primitives in total. */
+#define RT2_FLAG_INSTANCES_INLINE 64u /* two-level walk in one kernel: instance leaves in the TLAS, a lane that meets one switches
+                                   to the model space and the BLAS (always used by scenes too big to flatten); A/B and debugging */
+#define RT2_FLAG_NO_INSTANCE_SPLIT RT2_FLAG_INSTANCES_INLINE /* (round-2 name) */
+#define RT2_FLAG_INSTANCE_SPLIT 256u /* two passes: surfaces-only world tree, then one {ray, instance} entry per touched instance
+                                   (RT2_MAX_HOISTED_INSTANCES); measured equal to the inline walk, kept for A/B */
 
 typedef struct rt2_config {
   int32_t device;            /* CUDA device ordinal (the first one when n_gpus > 1) */
@@ -284,7 +296,7 @@ typedef struct rt2_stats {
   uint32_t instance_split;  /* 1 iff the two-pass instance split is active */
   double gpu_ms_extend_inst; /* instance split, while profiling: time of the instance pass (gpu_ms_extend = the world pass) */
   uint32_t max_stack_need;  /* stack entries the deepest traversal of this scene can need (tree depths, verified <= 63 at upload) */
-  uint32_t reserved;
+  uint32_t instance_mode;   /* 0 no instances, 1 inline TLAS -> BLAS, 2 two-pass split, 3 unified world tree, 4 flat extend */
 } rt2_stats;
 
 typedef struct rt2_hit {

@@ -25,7 +25,9 @@ RT2_FLAG_NO_FUSED_SHADE = 4
 RT2_FLAG_GPU_LBVH = 8
 RT2_FLAG_SORT_RAYS = 16
 RT2_FLAG_WIDE_BVH = 32
+RT2_FLAG_INSTANCES_INLINE = 64
 RT2_FLAG_NO_INSTANCE_SPLIT = 64
+RT2_FLAG_INSTANCE_SPLIT = 256
 RT2_FLAG_NO_FLAT_EXTEND = 128
 RT2_MAX_HOISTED_INSTANCES = 4
 RT2_ABI_VERSION = 3
@@ -102,6 +104,8 @@ class SceneDesc(C.Structure):
         ("background", C.c_float * 3), ("min_inv_scale", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
         ("camera", Camera),
         ("n_images", C.c_uint32), ("n_image_texels", C.c_uint32), ("images", C.POINTER(Image)), ("image_texels", C.POINTER(C.c_float)),
+        ("has_unified_tlas", C.c_uint32), ("tlas_unified_root", C.c_uint32), ("n_inst_leaves", C.c_uint32), ("pad_unified", C.c_uint32),
+        ("inst_leaves", C.POINTER(C.c_uint32)),
         ("has_world_tlas", C.c_uint32), ("tlas_world_root", C.c_uint32), ("inst_bounds", C.POINTER(C.c_float)),
     ]
 
@@ -119,7 +123,7 @@ class Stats(C.Structure):
                 ("gpu_ms_other", C.c_double), ("gpu_ms_finish", C.c_double), ("gpu_ms_bvh_build", C.c_double), ("box_pair_tests", C.c_uint64),
                 ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64), ("gpu_ms_sort", C.c_double),
                 ("stack_overflows", C.c_uint64), ("pending_frames", C.c_uint64), ("n_gpus", C.c_uint32), ("instance_split", C.c_uint32),
-                ("gpu_ms_extend_inst", C.c_double), ("max_stack_need", C.c_uint32), ("reserved", C.c_uint32)]
+                ("gpu_ms_extend_inst", C.c_double), ("max_stack_need", C.c_uint32), ("instance_mode", C.c_uint32)]
 
 
 class Hit(C.Structure):

@@ -162,10 +162,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse(const DeviceScene S, con
                                                         int fetch_threshold) {
   const uint32_t n = n_ptr ? *n_ptr : n_fixed;
   TravCounters cnt;
+  __shared__ float s_ms[kMode == kTravUnified ? 7 * kBlock : 1];  // kTravUnified: model-space ray of the instance last met
   // queues below the threshold were not sorted (rt_sort.cuh): consume them in queue order
   const uint32_t* ord = (order != nullptr && n >= sort_min_rays) ? order : nullptr;
   // scene.hittable_list.Hit(scene, r, Interval{0.001, kInfinity}, rec)  (RayTracer.cpp:25)
-  traverse_queue<M, kCount, kMode>(S, n, ray_o, ray_d, tmin, tmax, cursor, ord, trav, io, cnt, max_steps, fetch_threshold);
+  traverse_queue<M, kCount, kMode>(S, n, ray_o, ray_d, tmin, tmax, cursor, ord, trav, io, cnt, max_steps, fetch_threshold, s_ms);
   flush_trav_counters(cnt, kCount, totals);
 }
 
@@ -609,6 +610,9 @@ struct Renderer::Impl {
   void* d_inst_bounds{nullptr};
   size_t cap_flat_refs{0}, cap_flat_offsets{0}, cap_inst_bounds{0};
   bool flat_mode{false};  // tiny scene: k_traverse_flat instead of the BVH walk
+  bool unified_mode{false};  // instances flattened into ONE world-space tree (kTravUnified): the default when the scene carries it
+  void* d_inst_leaves{nullptr};
+  size_t cap_inst_leaves{0};
   bool split_mode{false};  // instance split: k_traverse<kTravWorld> + k_traverse<kTravInst> (1..kMaxHoistedInstances instances)
   SplitIO split{};         // entry queue / per-entry winner / per-ray merge slot (allocated in Resize when split_mode)
   size_t split_capacity{0};  // entries the queue holds (= paths per batch x instances)
@@ -676,7 +680,7 @@ Renderer::~Renderer() {
   cudaSetDevice(cfg_.device);
   FreeState();
   Impl& m = *impl_;
-  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_inst_bounds, m.d_images, m.d_image_texels, m.d_nodes4};
+  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_inst_bounds, m.d_images, m.d_image_texels, m.d_nodes4, m.d_inst_leaves};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.totals) cudaFree(m.totals);
@@ -933,10 +937,13 @@ int Renderer::UploadScene(const HostScene& scene) {
       tree_depths_.clear();
       tree_depths_.push_back(depth_of(scene.tlas_root));
       for (const rt2_instance& in : scene.instances) tree_depths_.push_back(depth_of(in.blas_root));
-      if (scene.has_world_tlas) tree_depths_.push_back(depth_of(scene.tlas_world_root));
+      world_depth_ = scene.has_world_tlas ? depth_of(scene.tlas_world_root) : 0u;
+      unified_depth_ = scene.has_unified_tlas ? depth_of(scene.tlas_unified_root) : 0u;
     }
     world_tree_ok_ = scene.has_world_tlas;
     world_root_ = scene.tlas_world_root;
+    unified_tree_ok_ = scene.has_unified_tlas;
+    unified_root_ = scene.tlas_unified_root;
     bvh_build_ms_ = 0;
     m.wide_mode = false;
     if (cfg_.flags & RT2_FLAG_WIDE_BVH) {
@@ -1066,9 +1073,22 @@ int Renderer::UploadScene(const HostScene& scene) {
     }
   }
   // instance split: the few instances are hoisted out of the world tree (rt_trace.cuh, kTravWorld / kTravInst)
+  // How instances are walked: unified world tree (default when the scene carries one), two-pass split (RT2_FLAG_INSTANCE_SPLIT,
+  // 1..4 instances) or inline TLAS -> BLAS (RT2_FLAG_INSTANCES_INLINE, and every scene too big to flatten).
+  const bool want_inline = (cfg_.flags & RT2_FLAG_INSTANCES_INLINE) != 0;
+  const bool want_split = (cfg_.flags & RT2_FLAG_INSTANCE_SPLIT) != 0 && !want_inline;
   const bool was_split = m.split_mode;
-  m.split_mode = !m.flat_mode && !m.wide_mode && !(cfg_.flags & RT2_FLAG_NO_INSTANCE_SPLIT) && world_tree_ok_ &&
-                 !scene.instances.empty() && scene.instances.size() <= kMaxHoistedInstances && d.inst_bounds != nullptr;
+  m.split_mode = !m.flat_mode && !m.wide_mode && want_split && world_tree_ok_ && !scene.instances.empty() &&
+                 scene.instances.size() <= kMaxHoistedInstances && d.inst_bounds != nullptr;
+  m.unified_mode = !m.flat_mode && !m.wide_mode && !want_inline && !m.split_mode && unified_tree_ok_ && !scene.instances.empty();
+  d.inst_leaves = nullptr;
+  d.tlas_unified_root = d.tlas_root;
+  if (m.unified_mode) {
+    rc = UploadBuf(m, &m.d_inst_leaves, &m.cap_inst_leaves, scene.inst_leaves, &err_);
+    if (rc != RT2_OK) return rc;
+    d.inst_leaves = static_cast<const uint2*>(m.d_inst_leaves);
+    d.tlas_unified_root = unified_root_;
+  }
   d.n_hoisted = m.split_mode ? static_cast<uint32_t>(scene.instances.size()) : 0u;
   d.tlas_world_root = m.split_mode ? world_root_ : d.tlas_root;
   {
@@ -1078,8 +1098,8 @@ int Renderer::UploadScene(const HostScene& scene) {
     uint32_t blas_max = 0;
     for (size_t i = 0; i < n_inst && 1 + i < tree_depths_.size(); i++) blas_max = std::max(blas_max, tree_depths_[1 + i]);
     const uint32_t tlas = tree_depths_.empty() ? 0u : tree_depths_[0];
-    const uint32_t world = (world_tree_ok_ && tree_depths_.size() == n_inst + 2) ? tree_depths_.back() : 0u;
-    max_stack_need_ = m.split_mode ? std::max(world, blas_max) : (n_inst ? tlas + 1 + blas_max : tlas);
+    const uint32_t world = world_tree_ok_ ? world_depth_ : 0u;
+    max_stack_need_ = m.unified_mode ? unified_depth_ : (m.split_mode ? std::max(world, blas_max) : (n_inst ? tlas + 1 + blas_max : tlas));
     if (max_stack_need_ > static_cast<uint32_t>(kStackSize - 1) && !m.flat_mode && !m.wide_mode) {
       err_ = "BVH too deep for the traversal stack: needs " + std::to_string(max_stack_need_) + " entries, the stack holds " +
              std::to_string(kStackSize - 1);
@@ -1124,7 +1144,10 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
       if (RT2_PRIM_TYPE(bp.ref) != RT2_PRIM_INSTANCE) surfaces.push_back(bp);
     trees.push_back(&surfaces);
   }
+  const bool want_unified_tree = scene.has_unified_tlas && !scene.unified_prims.empty();
+  if (want_unified_tree) trees.push_back(&scene.unified_prims);
   const size_t n_trees = trees.size();
+  const size_t world_slot = want_world_tree ? scene.tree_prims.size() : 0, unified_slot = want_unified_tree ? n_trees - 1 : 0;
   std::vector<uint32_t> pair_base(n_trees), ref_base(n_trees);
   uint64_t pairs = 0, refs = prefix.size();
   size_t max_n = 0;
@@ -1138,7 +1161,9 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
     if (k > 0 && k <= scene.instances.size()) instances[k - 1].blas_root = pair_base[k];
   }
   world_tree_ok_ = want_world_tree;
-  world_root_ = want_world_tree ? pair_base[n_trees - 1] : 0u;
+  world_root_ = want_world_tree ? pair_base[world_slot] : 0u;
+  unified_tree_ok_ = want_unified_tree;
+  unified_root_ = want_unified_tree ? pair_base[unified_slot] : 0u;
   if (pairs >= 0x7FFFFFF0ull || refs >= 0x03FFFFFFull) {
     err_ = "scene too large for the 26-bit primitive / 31-bit node index fields";
     return RT2_ERR_UNSUPPORTED;
@@ -1206,6 +1231,8 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
     RT2_CUDA(e);
     RT2_CUDA(e2);
   }
+  world_depth_ = want_world_tree ? tree_depths_[world_slot] : 0u;
+  unified_depth_ = want_unified_tree ? tree_depths_[unified_slot] : 0u;
   float ms = 0;
   cudaEventElapsedTime(&ms, m.ev_start, m.ev_stop);
   bvh_build_ms_ = ms;
@@ -1399,21 +1426,26 @@ static void LaunchExtendT(Renderer::Impl& m, const ExtendArgs& a, uint64_t* laun
   } else if (m.flat_mode) {
     k_traverse_flat<M><<<a.grid_flat, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.ray_o, a.ray_d, a.tmin, a.tmax, a.trav);
     (*launches)++;
+  } else if (m.unified_mode) {
+    k_traverse<M, kCount, kTravUnified><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
+                                                                            a.order, a.sort_min_rays, a.trav, SplitIO{}, m.totals,
+                                                                            m.trav_max_steps, m.trav_fetch_threshold);
+    (*launches)++;
   } else if (m.split_mode) {
     SplitIO io = a.io;
     io.entry_count = a.entry_count;
     k_traverse<M, kCount, kTravWorld><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
-                                                                       a.order, a.sort_min_rays, a.trav, io, m.totals, m.trav_max_steps,
-                                                                       m.trav_fetch_threshold);
+                                                                          a.order, a.sort_min_rays, a.trav, io, m.totals, m.trav_max_steps,
+                                                                          m.trav_fetch_threshold);
     if (mid) cudaEventRecord(mid, m.stream);  // profiling: world pass | instance pass
     k_traverse<M, kCount, kTravInst><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.entry_count, 0u, a.entry_cursor, a.ray_o, a.ray_d, a.tmin,
-                                                                      a.tmax, nullptr, 0u, a.trav, io, m.totals, m.trav_max_steps,
-                                                                      m.trav_fetch_threshold);
+                                                                         a.tmax, nullptr, 0u, a.trav, io, m.totals, m.trav_max_steps,
+                                                                         m.trav_fetch_threshold);
     *launches += 2;
   } else {
     k_traverse<M, kCount, kTravInline><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
-                                                                        a.order, a.sort_min_rays, a.trav, SplitIO{}, m.totals,
-                                                                        m.trav_max_steps, m.trav_fetch_threshold);
+                                                                           a.order, a.sort_min_rays, a.trav, SplitIO{}, m.totals,
+                                                                           m.trav_max_steps, m.trav_fetch_threshold);
     (*launches)++;
   }
 }
@@ -2093,6 +2125,7 @@ int Renderer::GetStats(rt2_stats* out) {
   out->pending_frames = pending_frames_;
   out->n_gpus = 1;
   out->instance_split = m.split_mode ? 1u : 0u;
+  out->instance_mode = m.flat_mode ? 4u : (m.unified_mode ? 3u : (m.split_mode ? 2u : (m.ds.n_instances ? 1u : 0u)));
   return RT2_OK;
 }
 

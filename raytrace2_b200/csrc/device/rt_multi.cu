@@ -319,6 +319,7 @@ int MultiRenderer::GetStats(rt2_stats* out) {
     out->gpu_ms_extend_inst = std::max(out->gpu_ms_extend_inst, s.gpu_ms_extend_inst);
     out->gpu_ms_bvh_build = std::max(out->gpu_ms_bvh_build, s.gpu_ms_bvh_build);
     out->instance_split = s.instance_split;
+    out->instance_mode = s.instance_mode;
     out->max_stack_need = std::max(out->max_stack_need, s.max_stack_need);
   }
   out->frames = frames_;

@@ -77,8 +77,12 @@ class Renderer {
   bool state_ok_{false};        // the frame buffers are allocated (false after a failed Resize)
   bool world_tree_ok_{false};   // the scene carries a surfaces-only world TLAS (instance split)
   uint32_t world_root_{0};
+  bool unified_tree_ok_{false};  // the scene carries the unified world tree (instances flattened into world-space leaves)
+  uint32_t unified_root_{0};
+  uint32_t unified_depth_{0};
+  uint32_t world_depth_{0};
   uint32_t n_textures_{0};
-  std::vector<uint32_t> tree_depths_;  // node-pair depth of every tree on the device ([0] TLAS, [1 + i] BLAS i, [last] world tree)
+  std::vector<uint32_t> tree_depths_;  // node-pair depth of the trees on the device: [0] TLAS, [1 + i] BLAS of instance i, ...
   uint32_t max_stack_need_{0};         // stack entries the deepest traversal of this scene can need (checked against kStackSize)
   uint64_t launches_{0};
   double gpu_ms_total_{0};

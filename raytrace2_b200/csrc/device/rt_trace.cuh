@@ -30,6 +30,8 @@ struct DeviceScene {
   const float4* __restrict__ nodes;  // 4 x float4 per node pair
   uint32_t tlas_root;        // world TLAS with the instances as singleton leaves (kTravInline)
   uint32_t tlas_world_root;  // world TLAS over surfaces only (kTravWorld: the instances are hoisted out of the tree)
+  uint32_t tlas_unified_root;  // world tree over surfaces + every instanced primitive as a world-space leaf (kTravUnified)
+  const uint2* __restrict__ inst_leaves;  // kTravUnified: {primitive reference, instance index} of instanced leaf k
   uint32_t n_hoisted;        // > 0: instance split — all n_instances (<= kMaxHoistedInstances) are hoisted
   uint32_t n_media;
   uint32_t n_instances;
@@ -247,6 +249,12 @@ struct TravCounters {
 //                finished, its segment [0, best.t * cull_scale] is tested against the world boxes of the (few, hoisted)
 //                instances — at the warp's convergence point, so all finished lanes do it together — and every touched
 //                instance becomes one entry {ray, instance} of the bounce's entry queue.
+//   kTravUnified ONE world-space tree whose leaves are the world surfaces and, each with a conservative world-space box,
+//                every primitive of every instance (DeviceScene::inst_leaves).  An instanced leaf is still tested in its
+//                instance's model space with the reference's arithmetic (the model-space ray is computed once per ray and
+//                instance and parked in shared memory), so the leaves and their raw t are exactly those of the two-level
+//                walks — but a ray bouncing inside an instance no longer walks the whole world tree first and the
+//                instance's tree second, and the closest hit found in either culls the other.
 //   kTravInst    pass 2: one lane = one entry.  The exact-arithmetic world-to-model transforms (Transform.cpp:13-20) run with
 //                the whole warp converged, the walk starts at the BLAS root with tmax = the ray's closest world surface,
 //                and a hit is merged into the ray's slot by a 64-bit atomicMin on (ordered t, entry index).
@@ -260,7 +268,7 @@ struct TravCounters {
 // lanes instead of whichever lanes happen to reach a leaf in the same iteration.  When fewer than `fetch_threshold` lanes
 // are busy the warp pulls new work from the queue with one atomic.  `order` (optional) is the permutation in which the
 // queue is consumed.  Results go to trav_out[ray] = {t bits, prim ref, instance, has-entries flag}.
-enum { kTravInline = 0, kTravWorld = 1, kTravInst = 2 };
+enum { kTravInline = 0, kTravWorld = 1, kTravInst = 2, kTravUnified = 3 };
 constexpr uint32_t kFetchChunk = 64;  // queue items a warp reserves with one atomic (big queues)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr uint32_t kTravDone = 0xFFFFFFFFu;  // `cur` of a lane whose ray is finished (carries kLeafFlag: phase 1 skips it)
@@ -313,14 +321,19 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
                                                const float4* __restrict__ ray_d, float tmin, float tmax,
                                                uint32_t* __restrict__ next_ray, const uint32_t* __restrict__ order,
                                                uint4* __restrict__ trav_out, const SplitIO& io, TravCounters& cnt,
-                                               int max_steps, int fetch_threshold) {
+                                               int max_steps, int fetch_threshold, float* __restrict__ ms_cache = nullptr) {
+  // ms_cache (kTravUnified): 7 x blockDim.x floats of shared memory — per thread the model-space ray (o, d, d.d) of the
+  // instance it last met
   const unsigned kFull = 0xFFFFFFFFu;
   const unsigned lane = threadIdx.x & 31u;
-  // stack[0] is a permanent bottom marker (kTravDone): popping it ends the ray without an emptiness test; stack[-1] exists
-  // so that the reload after that last pop stays inside the array
-  uint32_t stack_mem[kStackSize + 2];
-  uint32_t* const stack = stack_mem + 1;
-  int sp = 1;
+  // The traversal stack lives in local memory (L1-resident).  Slot 0 is never read as an entry (it absorbs the reload after
+  // the last pop), slot 1 holds a permanent bottom marker (kTravDone): popping it ends the ray without an emptiness test.
+  // (A shared-memory stack — one bank per thread, so a warp-wide push or pop is a single wavefront — measured no faster:
+  // 5 789 vs 5 814 Mrays/s, profiles/r02_notes.md.)
+  uint32_t stack[kStackSize + 2];
+  auto st_store = [&](int i, uint32_t v) { stack[i] = v; };
+  auto st_load = [&](int i) -> uint32_t { return stack[i]; };
+  int sp = 2;  // next free slot
   bool active = false;
   bool exhausted = false;
   uint32_t ray_idx = 0;
@@ -342,7 +355,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
     inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
     oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
   };
-  // The traversal stack lives in local memory (L1); `top` mirrors stack[sp - 1] in a register.  Every push / pop ends with an
+  // `top` mirrors the stack's top entry (slot sp - 1) in a register.  Every push / pop ends with an
   // unconditional reload of the new top, issued a whole node step before it can be needed, so a pop never waits for a load
   // and the node step below is branch-free: with 32 rays per warp some lane pushes and some lane pops in almost every step,
   // so predicating both costs no issue slots, while the branchy form ran the push at 3 and the pop at 5 of 32 lanes
@@ -354,7 +367,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
   auto pop_plain = [&]() {
     cur = top;
     sp -= 1;
-    top = stack[sp - 1];
+    top = st_load(sp - 1);
   };
   // Pops the next entry; the bottom marker means the ray is finished (published at the end of the round).
   auto pop = [&]() {
@@ -422,7 +435,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
               const float4 wo = ray_o[idx], wd = ray_d[idx];
               time = wo.w;
               set_space(make_f3(wo), make_f3(wd));
-              if (kMode == kTravInline) {
+              if (kMode == kTravInline || kMode == kTravUnified) {
                 // An instanced leaf reports t in model units (= world t * |M^-1 d|): a world-space box at parameter t_w can
                 // hold an instanced hit with raw t as small as t_w * sigma_min * |d|, so scale the TLAS culling bound.
                 cull_scale = (S.n_instances > 0) ? fmaxf(1.0f, 1.0f / (S.min_inv_scale * sqrtf(a))) : 1.0f;
@@ -430,12 +443,12 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
                 cur_inst = -1;
               }
               best.t = tmax;
-              cur = (kMode == kTravWorld) ? S.tlas_world_root : S.tlas_root;
+              cur = (kMode == kTravWorld) ? S.tlas_world_root : (kMode == kTravUnified ? S.tlas_unified_root : S.tlas_root);
             }
             best.prim = RT2_PRIM_NONE;
             best.instance = -1;
-            stack[0] = kTravDone;
-            sp = 1;
+            st_store(1, kTravDone);
+            sp = 2;
             top = kTravDone;
             active = true;
           }
@@ -450,11 +463,12 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
       // phase 1: interior nodes (at most max_steps per round, so that lanes holding a leaf do not wait for a long descent)
       for (int step = 0; step < max_steps && active && !(cur & kLeafFlag); step++) {
         const float4* np = S.nodes + static_cast<size_t>(cur) * 4;
+        // (one 256-bit load per node — LDG.E.256 on sm_100 — measured 4 % SLOWER than these four 128-bit loads; r02 notes)
         const float4 a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
         if (kCount) cnt.box_pairs++;
         // conservative culling: near is shrunk by 1e-6 relative before it is compared with far and with the (scaled)
         // closest hit so far; an empty slot has NaN bounds -> far is NaN -> never entered
-        const float bound = (kMode == kTravInline) ? best.t * cur_cull : best.t;
+        const float bound = (kMode == kTravInline) ? best.t * cur_cull : (kMode == kTravUnified ? best.t * cull_scale : best.t);
         float t0x = fmaf(a0.x, inv.x, oid.x), t1x = fmaf(a1.x, inv.x, oid.x);
         float t0y = fmaf(a0.y, inv.y, oid.y), t1y = fmaf(a1.y, inv.y, oid.y);
         float t0z = fmaf(a0.z, inv.z, oid.z), t1z = fmaf(a1.z, inv.z, oid.z);
@@ -477,19 +491,19 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         const bool both = h0 && h1, any = h0 || h1;
         const bool swap = both && (near1 < near0);
         const uint32_t near_child = (h0 && !swap) ? e0 : e1;
-        stack[sp] = swap ? e0 : e1;
+        st_store(sp, swap ? e0 : e1);
         if (kMode == kTravInline) {
           if (any) {
             cur = near_child;
             sp += both ? 1 : 0;
-            top = stack[sp - 1];
+            top = st_load(sp - 1);
           } else {
             pop();  // may have to leave an instance
           }
         } else {
           cur = any ? near_child : top;
           sp += any ? (both ? 1 : 0) : -1;
-          top = stack[sp - 1];
+          top = st_load(sp - 1);
         }
       }
       __syncwarp();
@@ -508,7 +522,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
             if (sphere_hit<M>(__ldg(S.spheres + 2 * idx), __ldg(S.spheres + 2 * idx + 1), o, d, a, time, tmin, best.t, t)) {
               best.t = t;
               best.prim = ref;
-              best.instance = cur_inst;
+              best.instance = (kMode == kTravUnified) ? -1 : cur_inst;  // kTravUnified: cur_inst is the cached instance
             }
           } else if (type == RT2_PRIM_QUAD) {
             if (kCount) cnt.quads++;
@@ -516,7 +530,39 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
             if (quad_hit<M>(S.quads + 5 * idx, o, d, tmin, best.t, t) && quad_wins_tie(S, t, ref, best)) {
               best.t = t;
               best.prim = ref;
-              best.instance = cur_inst;
+              best.instance = (kMode == kTravUnified) ? -1 : cur_inst;
+            }
+          } else if (kMode == kTravUnified) {
+            // instanced leaf: primitive il.x of instance il.y, tested in the instance's model space (Transform.cpp:13-20,75-88)
+            const uint2 il = __ldg(S.inst_leaves + idx);
+            float* ms = ms_cache + threadIdx.x;
+            if (cur_inst != static_cast<int32_t>(il.y)) {
+              if (kCount) cnt.instances++;
+              const uint4 in = __ldg(S.instances + il.y);
+              const RaySpace r = to_chain_space<M>(S, in.x, in.y, RaySpace{o, d});
+              ms[0 * blockDim.x] = r.o.x, ms[1 * blockDim.x] = r.o.y, ms[2 * blockDim.x] = r.o.z;
+              ms[3 * blockDim.x] = r.d.x, ms[4 * blockDim.x] = r.d.y, ms[5 * blockDim.x] = r.d.z;
+              ms[6 * blockDim.x] = vdot<M>(r.d, r.d);
+              cur_inst = static_cast<int32_t>(il.y);
+            }
+            const F3 mo = {ms[0 * blockDim.x], ms[1 * blockDim.x], ms[2 * blockDim.x]};
+            const F3 md = {ms[3 * blockDim.x], ms[4 * blockDim.x], ms[5 * blockDim.x]};
+            const uint32_t pidx = RT2_PRIM_INDEX(il.x);
+            float t;
+            if (RT2_PRIM_TYPE(il.x) == RT2_PRIM_SPHERE) {
+              if (kCount) cnt.spheres++;
+              if (sphere_hit<M>(__ldg(S.spheres + 2 * pidx), __ldg(S.spheres + 2 * pidx + 1), mo, md, ms[6 * blockDim.x], time, tmin, best.t, t)) {
+                best.t = t;
+                best.prim = il.x;
+                best.instance = static_cast<int32_t>(il.y);
+              }
+            } else {
+              if (kCount) cnt.quads++;
+              if (quad_hit<M>(S.quads + 5 * pidx, mo, md, tmin, best.t, t) && quad_wins_tie(S, t, il.x, best)) {
+                best.t = t;
+                best.prim = il.x;
+                best.instance = static_cast<int32_t>(il.y);
+              }
             }
           } else if (kMode == kTravInline) {
             // instance leaf (always a singleton leaf of the TLAS, host/bvh_build.cpp): enter its BLAS in model space
@@ -527,7 +573,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
             set_space(ms.o, ms.d);
             cur_inst = static_cast<int32_t>(idx);
             cur_cull = 1.0f;
-            stack[sp++] = kStackSentinel;
+            st_store(sp++, kStackSentinel);
             top = kStackSentinel;
             cur = in.z;
             entered = true;

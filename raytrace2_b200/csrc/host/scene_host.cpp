@@ -360,10 +360,51 @@ Box3 PrimBounds(const HostScene& sc, uint32_t ref) {
   return b;
 }
 
+constexpr size_t kMaxUnifiedLeaves = 1u << 22;
+
 struct Flattener {
   HostScene* sc;
   const std::vector<PrimDef>* prims;
   std::vector<BuildPrim> tlas;
+  std::vector<BuildPrim> unified_leaves;  // the instanced primitives as world-space leaves (see HostScene::inst_leaves)
+
+  // Conservative world-space box of primitive `ref` under the instance chain (outermost level first).
+  Box3 InstancedPrimWorldBounds(uint32_t ref, const std::vector<M4>& chain, double sigma_max) const {
+    Box3 b;
+    auto to_world = [&](V3 p) {
+      for (size_t l = chain.size(); l-- > 0;) p = MulPoint(chain[l], p);
+      return p;
+    };
+    const uint32_t i = RT2_PRIM_INDEX(ref);
+    if (RT2_PRIM_TYPE(ref) == RT2_PRIM_SPHERE) {
+      // a sphere maps to an ellipsoid inside the ball of radius r * sigma_max(chain) around the mapped centre
+      const rt2_sphere& s = sc->spheres[i];
+      const float r = static_cast<float>(std::fabs(s.radius) * sigma_max * 1.000001);
+      for (int e = 0; e < 2; e++) {
+        const V3 c = to_world(V3{s.center0[0] + s.displacement[0] * static_cast<float>(e), s.center0[1] + s.displacement[1] * static_cast<float>(e),
+                                 s.center0[2] + s.displacement[2] * static_cast<float>(e)});
+        const float lo[3] = {c.x - r, c.y - r, c.z - r}, hi[3] = {c.x + r, c.y + r, c.z + r};
+        b.Grow(lo);
+        b.Grow(hi);
+      }
+    } else {
+      const rt2_quad& q = sc->quads[i];
+      for (int cu = 0; cu < 2; cu++)
+        for (int cv = 0; cv < 2; cv++) {
+          const V3 w = to_world(V3{q.q[0] + (cu ? q.u[0] : 0.f) + (cv ? q.v[0] : 0.f), q.q[1] + (cu ? q.u[1] : 0.f) + (cv ? q.v[1] : 0.f),
+                                   q.q[2] + (cu ? q.u[2] : 0.f) + (cv ? q.v[2] : 0.f)});
+          const float p[3] = {w.x, w.y, w.z};
+          b.Grow(p);
+        }
+    }
+    for (int k = 0; k < 3; k++) {
+      const float ext = std::fmax(std::fabs(b.mn[k]), std::fabs(b.mx[k]));
+      const float pad = ext * 2e-6f + 1e-4f;
+      b.mn[k] -= pad;
+      b.mx[k] += pad;
+    }
+    return b;
+  }
 
   static BuildPrim MakeBuildPrim(const Box3& b, uint32_t ref) {
     BuildPrim p;
@@ -487,6 +528,20 @@ struct Flattener {
     double sigma = 1.0;
     for (size_t i = sigma_first; i < level_sigma_.size(); i++) sigma *= level_sigma_[i];
     sc->min_inv_scale = std::fmin(sc->min_inv_scale, static_cast<float>(sigma * 0.9999));
+    // unified world tree: this instance's primitives as world-space leaves (sigma = sigma_min of the inverse chain, so
+    // 1 / sigma bounds the largest stretch of the model matrix)
+    if (sigma > 0.0) {
+      const uint32_t inst_idx = static_cast<uint32_t>(sc->instances.size() - 1);
+      for (const BuildPrim& p : own) {
+        if (RT2_PRIM_TYPE(p.ref) != RT2_PRIM_SPHERE && RT2_PRIM_TYPE(p.ref) != RT2_PRIM_QUAD) continue;
+        const uint32_t k = static_cast<uint32_t>(sc->inst_leaves.size() / 2);
+        sc->inst_leaves.push_back(p.ref);
+        sc->inst_leaves.push_back(inst_idx);
+        unified_leaves.push_back(MakeBuildPrim(InstancedPrimWorldBounds(p.ref, chain, 1.0 / sigma), (RT2_PRIM_INSTANCE << 28) | k));
+      }
+    } else {
+      unified_ok = false;  // singular transform: no finite world bound
+    }
     // world bounds: the 8 corners through the chain, innermost level first (p_world = M_0 * (M_1 * ... p))
     Box3 world;
     for (int ci = 0; ci < 8; ci++) {
@@ -509,6 +564,7 @@ struct Flattener {
   }
 
   std::vector<double> level_sigma_;
+  bool unified_ok{true};
 };
 
 int Compile(Builder& b, std::string* err) {
@@ -540,7 +596,7 @@ int Compile(Builder& b, std::string* err) {
     };
     for (const ReplayItem& it : ref_order) rank_node(b.top[it.idx], rank_node);
   }
-  Flattener fl{sc, &b.prims, {}, {}};
+  Flattener fl{sc, &b.prims, {}, {}, {}};
   sc->min_inv_scale = 1.0f;
   for (size_t i = 0; i < b.top.size(); i++) fl.FlattenNode(b.top[i], {}, &fl.tlas, static_cast<uint32_t>(i));
   sc->tlas_root = BuildBVH(fl.tlas, sc);
@@ -554,6 +610,17 @@ int Compile(Builder& b, std::string* err) {
       if (RT2_PRIM_TYPE(p.ref) != RT2_PRIM_INSTANCE) surfaces.push_back(p);
     sc->tlas_world_root = BuildBVH(surfaces, sc);
     sc->has_world_tlas = true;
+  }
+  // unified world tree: the world surfaces + every instanced primitive as a world-space leaf
+  sc->has_unified_tlas = false;
+  if (!sc->instances.empty() && fl.unified_ok && !fl.unified_leaves.empty() && fl.unified_leaves.size() <= kMaxUnifiedLeaves) {
+    std::vector<BuildPrim> all;
+    for (const BuildPrim& p : fl.tlas)
+      if (RT2_PRIM_TYPE(p.ref) != RT2_PRIM_INSTANCE) all.push_back(p);
+    all.insert(all.end(), fl.unified_leaves.begin(), fl.unified_leaves.end());
+    sc->unified_prims = all;
+    sc->tlas_unified_root = BuildBVH(all, sc);
+    sc->has_unified_tlas = true;
   }
   sc->UpdateCamera();
   (void)err;
@@ -971,6 +1038,11 @@ void HostScene::FillDesc(rt2_scene_desc* d) const {
   d->n_image_texels = static_cast<uint32_t>(image_texels.size() / 4);
   d->images = images.data();
   d->image_texels = image_texels.data();
+  d->has_unified_tlas = has_unified_tlas ? 1u : 0u;
+  d->tlas_unified_root = tlas_unified_root;
+  d->n_inst_leaves = static_cast<uint32_t>(inst_leaves.size() / 2);
+  d->pad_unified = 0;
+  d->inst_leaves = inst_leaves.data();
   d->has_world_tlas = has_world_tlas ? 1u : 0u;
   d->tlas_world_root = tlas_world_root;
   d->inst_bounds = inst_bounds.data();

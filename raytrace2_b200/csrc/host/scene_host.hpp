@@ -48,6 +48,15 @@ struct HostScene {
   uint32_t tlas_world_root{0};
   bool has_world_tlas{false};
   std::vector<float> inst_bounds;  // 8 floats per instance: conservative world-space AABB (min xyz 0, max xyz 0)
+  // Unified world tree (device/rt_trace.cuh kTravUnified): every primitive of every instance is ALSO a leaf of one world-space
+  // tree, with a conservative world-space box; leaf reference (RT2_PRIM_INSTANCE << 28 | k) names inst_leaves[k] =
+  // {primitive reference, instance index}.  The primitive is still tested in the instance's model space, so hits are the
+  // ones the two-level walk reports — only the culling structure is flat.  Built when the instances hold <= kMaxUnifiedLeaves
+  // primitives in total.
+  std::vector<uint32_t> inst_leaves;  // 2 per instanced leaf
+  uint32_t tlas_unified_root{0};
+  bool has_unified_tlas{false};
+  std::vector<BuildPrim> unified_prims;  // build input of the unified tree (device LBVH build)
   uint32_t n_top_level{0};
   std::vector<uint8_t> span1_flags;  // per top-level node (Q2)
   // Leaf records of every tree, kept for the device-side LBVH build (RT2_FLAG_GPU_LBVH): [0] = world TLAS,

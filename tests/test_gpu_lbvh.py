@@ -80,6 +80,8 @@ def test_device_built_tree_is_valid_and_gives_identical_hits(native_lib, name):
     sizes = [count_leaves(d.tlas_root)] + [count_leaves(int(i["blas_root"])) for i in scene.instances()]
     if d.has_world_tlas:  # instance split: one more world tree over the surfaces only, laid out last
         sizes.append(count_leaves(d.tlas_world_root))
+    if d.has_unified_tlas:  # ... and the unified world tree (surfaces + instanced primitives as world-space leaves)
+        sizes.append(count_leaves(d.tlas_unified_root))
     roots, base = [], 0
     for n in sizes:
         roots.append(base)

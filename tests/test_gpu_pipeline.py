@@ -55,9 +55,9 @@ def test_flat_and_bvh_extend_agree(native_lib, name):
     scene = rt.Scene.load(scene_path(name))
     o, d, _ = fixed_rays(scene, 60000, seed=9)
     tf = rt.RayTracer(scene, dims=(64, 64))
-    tb = rt.RayTracer(scene, dims=(64, 64), flags=rt.RT2_FLAG_NO_FLAT_EXTEND)  # 2 instances: the two-pass instance split
+    tb = rt.RayTracer(scene, dims=(64, 64), flags=rt.RT2_FLAG_NO_FLAT_EXTEND)  # the BVH walk over the unified world tree
     n_inst = len(scene.instances())  # the Cornell boxes are instances; box-bounded media under a transform are not
-    assert tb.stats()["instance_split"] == (1 if 1 <= n_inst <= 4 else 0) and tf.stats()["instance_split"] == 0
+    assert tb.stats()["instance_mode"] == (3 if n_inst else 0) and tf.stats()["instance_mode"] == 4
     f = tf.intersect(o, d, skip_media=True)
     b = tb.intersect(o, d, skip_media=True)
     assert np.array_equal(f["material"] >= 0, b["material"] >= 0)

@@ -28,45 +28,53 @@ def _bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-# ---- instance split ------------------------------------------------------------------------------------------------
+# ---- instances: unified world tree (default), two-pass split, inline TLAS -> BLAS ----------------------------------------
+UNIFIED, SPLIT, INLINE = 0, rt.RT2_FLAG_INSTANCE_SPLIT, rt.RT2_FLAG_INSTANCES_INLINE
+
+
 @pytest.mark.parametrize("name,extra", [(BOOK2, 0), ("cornell_box_scene_graph", rt.RT2_FLAG_NO_FLAT_EXTEND),
                                         ("cornell_box4", rt.RT2_FLAG_NO_FLAT_EXTEND), (BOOK2, rt.RT2_FLAG_GPU_LBVH)])
-def test_instance_split_reports_the_same_hits_as_the_inline_walk(native_lib, name, extra):
+def test_all_instance_walks_report_the_same_hits(native_lib, name, extra):
+    """The closest hit is an arg-min over the same leaves with the same model-space arithmetic in all three walks: the unified
+    world tree, the two-pass split and the inline two-level walk must agree bit for bit (exact cross-space ties aside)."""
     scene = rt.Scene.load(scene_path(name))
     n_inst = len(scene.instances())
     assert 1 <= n_inst <= 4
     o, d, tm = fixed_rays(scene, 200000, seed=17)
-    split = rt.RayTracer(scene, flags=extra, dims=(32, 32))
-    inline = rt.RayTracer(scene, flags=extra | rt.RT2_FLAG_NO_INSTANCE_SPLIT, dims=(32, 32))
-    assert split.stats()["instance_split"] == 1 and inline.stats()["instance_split"] == 0
-    a = split.intersect(o, d, tm, skip_media=True)
-    b = inline.intersect(o, d, tm, skip_media=True)
-    assert np.array_equal(a["material"] >= 0, b["material"] >= 0)
+    res = {}
+    for label, flag, mode in (("unified", UNIFIED, 3), ("split", SPLIT, 2), ("inline", INLINE, 1)):
+        tr = rt.RayTracer(scene, flags=extra | flag, dims=(32, 32))
+        assert tr.stats()["instance_mode"] == mode, (label, tr.stats()["instance_mode"])
+        res[label] = tr.intersect(o, d, tm, skip_media=True)
+    a = res["unified"]
     hit = a["material"] >= 0
     assert hit.sum() > 50000 and (a["instance"][hit] >= 0).sum() > 500, "the rays must exercise the instances"
-    # the closest hit is an arg-min over leaves: both walks must agree bit for bit (exact cross-space ties aside)
-    same = (_bits(a["t"]) == _bits(b["t"])) & (a["prim"] == b["prim"]) & (a["instance"] == b["instance"])
-    assert (~same[hit]).sum() <= 2e-5 * hit.sum(), int((~same[hit]).sum())
-    ok = hit & same
-    for key in ("point", "normal"):
-        assert np.array_equal(_bits(a[key][ok]), _bits(b[key][ok]))
-    assert np.array_equal(a["front_face"][ok], b["front_face"][ok])
+    for other in ("split", "inline"):
+        b = res[other]
+        assert np.array_equal(hit, b["material"] >= 0), other
+        same = (_bits(a["t"]) == _bits(b["t"])) & (a["prim"] == b["prim"]) & (a["instance"] == b["instance"])
+        assert (~same[hit]).sum() <= 2e-5 * hit.sum(), (other, int((~same[hit]).sum()))
+        ok = hit & same
+        for key in ("point", "normal"):
+            assert np.array_equal(_bits(a[key][ok]), _bits(b[key][ok])), (other, key)
+        assert np.array_equal(a["front_face"][ok], b["front_face"][ok])
 
 
-def test_instance_split_renders_the_same_image(native_lib):
+def test_all_instance_walks_render_the_same_image(native_lib):
     dims, spp = (200, 200), 16
     scene = rt.Scene.load(scene_path(BOOK2), perlin_seed=5)
     kw = dict(num_samples=spp, max_depth=50, seed=77, dims=dims)
-    a = rt.RayTracer(scene, **kw)
-    b = rt.RayTracer(scene, flags=rt.RT2_FLAG_NO_INSTANCE_SPLIT, **kw)
-    a.Update(spp)
-    b.Update(spp)
-    ia, ib = a.read_accum(), b.read_accum()
-    ra, rb = a.stats()["rays"], b.stats()["rays"]
-    assert abs(ra - rb) <= 2e-5 * ra, (ra, rb)
-    same = np.all(_bits(ia) == _bits(ib), axis=-1)
-    assert same.mean() > 0.999, same.mean()  # identical hits -> identical paths (same Philox keys)
-    assert a.stats()["launches"] > b.stats()["launches"]  # one more kernel per bounce
+    img, rays, launches = {}, {}, {}
+    for label, flag in (("unified", UNIFIED), ("split", SPLIT), ("inline", INLINE)):
+        tr = rt.RayTracer(scene, flags=flag, **kw)
+        tr.Update(spp)
+        img[label] = tr.read_accum()
+        rays[label], launches[label] = tr.stats()["rays"], tr.stats()["launches"]
+    for other in ("split", "inline"):
+        assert abs(rays["unified"] - rays[other]) <= 2e-5 * rays["unified"], (other, rays)
+        same = np.all(_bits(img["unified"]) == _bits(img[other]), axis=-1)
+        assert same.mean() > 0.999, (other, same.mean())  # identical hits -> identical paths (same Philox keys)
+    assert launches["split"] > launches["inline"] == launches["unified"]  # the split adds one kernel per bounce
 
 
 # ---- deferred Update -------------------------------------------------------------------------------------------------
@@ -356,7 +364,7 @@ def test_cornell_full_size_1024spp_against_reference_tiles(native_lib):
 def test_tree_depths_fit_the_traversal_stack(native_lib):
     """The walks keep one stack entry per tree level and do no bounds checks; rt2_create / rt2_upload_scene compute the depth of
     every tree on the device (host SAH trees and device LBVH trees alike) and refuse a scene that does not fit."""
-    for name, flags in [(BOOK2, 0), (BOOK2, rt.RT2_FLAG_NO_INSTANCE_SPLIT), (BOOK2, rt.RT2_FLAG_GPU_LBVH),
+    for name, flags in [(BOOK2, 0), (BOOK2, INLINE), (BOOK2, SPLIT), (BOOK2, rt.RT2_FLAG_GPU_LBVH), (BOOK2, rt.RT2_FLAG_GPU_LBVH | INLINE),
                         ("final_render_book_1", rt.RT2_FLAG_GPU_LBVH), ("cornell_box4", rt.RT2_FLAG_NO_FLAT_EXTEND)]:
         tr = rt.RayTracer(rt.Scene.load(scene_path(name)), num_samples=4, dims=(160, 90), flags=flags)
         tr.Update(4)
@@ -365,9 +373,8 @@ def test_tree_depths_fit_the_traversal_stack(native_lib):
         assert 1 <= st["max_stack_need"] <= 63 and st["stack_overflows"] == 0, (name, flags, st["max_stack_need"])
     # the inline walk nests TLAS + sentinel + BLAS on one stack; the split walks need only the deeper of the two trees
     scene = rt.Scene.load(scene_path(BOOK2))
-    split = rt.RayTracer(scene, dims=(32, 32)).stats()["max_stack_need"]
-    inline = rt.RayTracer(scene, dims=(32, 32), flags=rt.RT2_FLAG_NO_INSTANCE_SPLIT).stats()["max_stack_need"]
-    assert inline > split
+    need = {f: rt.RayTracer(scene, dims=(32, 32), flags=f).stats()["max_stack_need"] for f in (UNIFIED, SPLIT, INLINE)}
+    assert need[INLINE] > need[SPLIT] and need[INLINE] > need[UNIFIED]
 
 
 def test_duplicate_keys_do_not_make_a_deep_lbvh(native_lib):

@@ -93,25 +93,45 @@ def _check_bvh(scene):
     for r in roots:
         walk(r, None, None, 0)
     n_inst = len(scene.instances())
-    world_only = np.zeros(len(refs), np.int32)
+    tlas_slots = _leaf_ref_slots(nodes, int(d.tlas_root))
+    surfaces = sorted(int(refs[i]) for i in tlas_slots if (int(refs[i]) >> 28) != _capi.RT2_PRIM_INSTANCE)
+    extra = np.zeros(len(refs), np.int32)
     if d.has_world_tlas:
         # instance split: a second world tree over the same surfaces, without the instance leaves
         assert 1 <= n_inst <= _capi.RT2_MAX_HOISTED_INSTANCES
         before = seen.copy()
         walk(int(d.tlas_world_root), None, None, 0)
         world_only = seen - before
-        seen = before
-        via_tlas = sorted(int(refs[i]) for i in range(len(refs)) if before[i] and (int(refs[i]) >> 28) != _capi.RT2_PRIM_INSTANCE
-                          and i in _leaf_ref_slots(nodes, int(d.tlas_root)))
-        via_world = sorted(int(refs[i]) for i in range(len(refs)) if world_only[i])
-        assert via_tlas == via_world, "the surfaces-only world tree must hold exactly the TLAS's non-instance leaves"
-        assert all((r >> 28) != _capi.RT2_PRIM_INSTANCE for r in via_world)
+        seen[:] = before
+        extra += world_only
+        assert sorted(int(refs[i]) for i in range(len(refs)) if world_only[i]) == surfaces, \
+            "the surfaces-only world tree must hold exactly the TLAS's non-instance leaves"
         b = np.ctypeslib.as_array(d.inst_bounds, shape=(n_inst, 8))
         assert np.all(b[:, 0:3] < b[:, 4:7])
     else:
         assert n_inst == 0 or n_inst > _capi.RT2_MAX_HOISTED_INSTANCES
+    if d.has_unified_tlas:
+        # unified world tree: the surfaces + every instanced primitive once, as leaf (INSTANCE << 28 | k) -> inst_leaves[k]
+        before = seen.copy()
+        walk(int(d.tlas_unified_root), None, None, 0)
+        uni = seen - before
+        seen[:] = before
+        extra += uni
+        got = sorted(int(refs[i]) for i in range(len(refs)) if uni[i])
+        inst_refs = [r for r in got if (r >> 28) == _capi.RT2_PRIM_INSTANCE]
+        assert [r for r in got if (r >> 28) != _capi.RT2_PRIM_INSTANCE] == surfaces
+        assert [r & 0x0FFFFFFF for r in inst_refs] == list(range(d.n_inst_leaves)) and d.n_inst_leaves > 0
+        leaves = np.ctypeslib.as_array(d.inst_leaves, shape=(d.n_inst_leaves, 2))
+        assert np.all(leaves[:, 1] < n_inst) and np.all((leaves[:, 0] >> 28) <= _capi.RT2_PRIM_QUAD)
+        # every BLAS primitive of every instance appears exactly once
+        want = []
+        for j, inst in enumerate(scene.instances()):
+            want += [(int(refs[i]), j) for i in _leaf_ref_slots(nodes, int(inst["blas_root"]))]
+        assert sorted(want) == sorted((int(a), int(b)) for a, b in leaves)
+    else:
+        assert n_inst == 0
     for i in range(len(refs)):
-        assert seen[i] + world_only[i] == (0 if i in media_refs else 1), f"prim ref {i} referenced {seen[i]} times"
+        assert seen[i] + extra[i] == (0 if i in media_refs else 1), f"prim ref {i} referenced {seen[i] + extra[i]} times"
 
 
 def _leaf_ref_slots(nodes, root):

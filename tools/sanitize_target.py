@@ -27,7 +27,7 @@ def main():
     done = []
     book2 = scene("book2_final_scene_10000_samples")
     o, d, t = fixed_rays(book2, 3000, seed=1)
-    for label, flags in [("split", 0), ("inline", rt.RT2_FLAG_NO_INSTANCE_SPLIT), ("lbvh", rt.RT2_FLAG_GPU_LBVH),
+    for label, flags in [("unified", 0), ("split", rt.RT2_FLAG_INSTANCE_SPLIT), ("inline", rt.RT2_FLAG_INSTANCES_INLINE), ("lbvh", rt.RT2_FLAG_GPU_LBVH),
                          ("per-bin", rt.RT2_FLAG_NO_FUSED_SHADE), ("fast-math", rt.RT2_FLAG_FAST_MATH)]:
         tr = rt.RayTracer(book2, num_samples=4, max_depth=12, seed=2, flags=flags | rt.RT2_FLAG_MOMENTS, dims=(48, 48), frames_per_batch=2)
         tr.intersect(o, d, t)
