@@ -369,6 +369,11 @@ int rt2_texture_value(rt2_renderer* r, uint32_t tex_idx, const float* points, co
 int rt2_read_bvh(rt2_renderer* r, rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs, size_t max_refs, uint32_t* n_pairs,
                  uint32_t* n_refs, uint32_t* tlas_root);
 int rt2_get_stats(rt2_renderer* r, rt2_stats* out);
+/* Device-side self checks.  compute-sanitizer is not available on every GPU pool, so a `make DEBUG_CHECKS=1` build of this
+ * library (libraytrace2_b200_dbg.so) verifies every data-dependent index in the kernels (node, primitive, material, queue,
+ * entry, stack ...) and counts violations per kind; it also poisons the wavefront buffers with NaN patterns at allocation.
+ * counters: 16 x uint64 (first GPU of the handle); *enabled = 1 iff the library was built with the checks. */
+int rt2_debug_counters(rt2_renderer* r, uint64_t* counters, int* enabled);
 int rt2_set_profiling(rt2_renderer* r, int enabled); /* per-kernel CUDA-event timing (serialises launches) */
 /* CUDA stream the renderer launches on (cudaStream_t as void*), for external event timing. */
 int rt2_stream(rt2_renderer* r, void** stream);

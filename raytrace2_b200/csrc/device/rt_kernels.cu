@@ -125,6 +125,7 @@ __device__ __forceinline__ void bin_push(uint32_t* __restrict__ counters, uint32
   if (static_cast<int>(lane) == leader) base = atomicAdd(&counters[1 + bin], __popc(peers));
   base = __shfl_sync(peers, base, leader);
   const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+  RT2_CHECK(pos < queue_stride && bin >= 0 && bin < kNumBins, kChkBin);
   queues[static_cast<size_t>(bin) * queue_stride + pos] = value;
 }
 
@@ -283,6 +284,8 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) k_finish_shade(const Device
       const uint4 tr = load_closest(S, trav, io, i);
       const float4 st = state[i];
       const uint32_t slot = __float_as_uint(st.w);
+      RT2_CHECK(slot < bins.stride, kChkSlot);  // bins.stride = paths per batch = slots of the radiance buffer
+      RT2_CHECK(o.x == o.x && d.x == d.x && st.x == st.x && __uint_as_float(tr.x) == __uint_as_float(tr.x), kChkNaN);
       const RngKey key = key_of_slot(fp, slot);
       HitOut h;
       if (kMedia) {
@@ -302,8 +305,10 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) k_finish_shade(const Device
         // miss: T * background (RayTracer.cpp:25-27)
         radiance[slot] = make_float4(st.x * S.background[0], st.y * S.background[1], st.z * S.background[2], 0.0f);
       } else {
+        RT2_CHECK(static_cast<uint32_t>(h.material) < S.n_materials, kChkMaterial);
         const float4 m0 = __ldg(S.materials + 2 * h.material), m1 = __ldg(S.materials + 2 * h.material + 1);
         const uint32_t type = __float_as_uint(m0.x);
+        RT2_CHECK(type < RT2_MAT_INVALID, kChkMaterial);
         if (__float_as_uint(m1.w) != 0u) {
           // deferred (noise-textured): record + bin, shaded by the per-bin kernels
           hit0[i] = make_float4(h.p.x, h.p.y, h.p.z, __uint_as_float(pack_uv16(h.u, h.v)));
@@ -381,6 +386,7 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) k_finish_shade(const Device
     __syncthreads();
     if (emit) {
       const uint32_t dst = s_base[parity] + off[cls][warp] + __popc(my_mask & ((1u << lane) - 1u));
+      RT2_CHECK(dst < bins.stride, kChkQueue);
       out_o[dst] = no;
       out_d[dst] = nd;
       out_state[dst] = ns;
@@ -970,6 +976,13 @@ int Renderer::UploadScene(const HostScene& scene) {
   d.images = static_cast<const uint4*>(m.d_images);
   d.image_texels = static_cast<const float4*>(m.d_image_texels);
   d.n_images = static_cast<uint32_t>(scene.images.size());
+  d.n_spheres = static_cast<uint32_t>(scene.spheres.size());
+  d.n_quads = static_cast<uint32_t>(scene.quads.size());
+  d.n_materials = static_cast<uint32_t>(scene.materials.size());
+  d.n_textures = static_cast<uint32_t>(scene.textures.size());
+  d.n_node_pairs = n_node_pairs_;
+  d.n_prim_refs = n_prim_refs_;
+  d.n_inst_leaves = static_cast<uint32_t>(scene.inst_leaves.size() / 2);
   d.materials = static_cast<const float4*>(m.d_materials);
   d.textures = static_cast<const float4*>(m.d_textures);
   d.perlin = static_cast<const rt2_perlin*>(m.d_perlin);
@@ -1292,6 +1305,7 @@ int Renderer::AllocSplitState() {
   RT2_CUDA(cudaMalloc(&m.split.entry_prim, cap * sizeof(uint32_t)));
   RT2_CUDA(cudaMalloc(&m.split.inst_best, N * sizeof(unsigned long long)));
   m.split_capacity = cap;
+  m.split.capacity = static_cast<uint32_t>(cap);
   return RT2_OK;
 }
 
@@ -1380,7 +1394,37 @@ int Renderer::AllocState() {
     RT2_CUDA(cudaMalloc(&m.sort_bin_base, kSortBins * sizeof(uint32_t)));
   }
 #endif
+#ifdef RT2_DEBUG_CHECKS
+  // poison: a kernel that reads wavefront state nobody wrote produces NaNs (bit pattern 0xFF..) instead of plausible zeros
+  for (int i = 0; i < 2; i++) {
+    RT2_CUDA(cudaMemset(m.ray_o[i], 0xFF, N * sizeof(float4)));
+    RT2_CUDA(cudaMemset(m.ray_d[i], 0xFF, N * sizeof(float4)));
+    RT2_CUDA(cudaMemset(m.state[i], 0xFF, N * sizeof(float4)));
+  }
+  RT2_CUDA(cudaMemset(m.hit0, 0xFF, N * sizeof(float4)));
+  RT2_CUDA(cudaMemset(m.hit1, 0xFF, N * sizeof(float4)));
+  RT2_CUDA(cudaMemset(m.trav, 0xFF, N * sizeof(uint4)));
+  RT2_CUDA(cudaMemset(m.bins.base, 0xFF, N * kNumBins * sizeof(uint32_t)));
+  RT2_CUDA(cudaMemset(m.mean_rgb, 0xFF, P * 3 * sizeof(float)));
+#endif
   if (m.split_mode) return AllocSplitState();
+  return RT2_OK;
+}
+
+// DEBUG_CHECKS builds: the violation counters of the device-side self checks (rt_trace.cuh); all zero otherwise.
+int Renderer::DebugCounters(uint64_t* out, int* enabled) {
+  for (int k = 0; k < 16; k++) out[k] = 0;
+#ifdef RT2_DEBUG_CHECKS
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  RT2_CUDA(cudaStreamSynchronize(m.stream));
+  unsigned long long v[kChkCount];
+  RT2_CUDA(cudaMemcpyFromSymbol(v, g_rt2_violations, sizeof(v)));
+  for (int k = 0; k < kChkCount && k < 16; k++) out[k] = v[k];
+  *enabled = 1;
+#else
+  *enabled = 0;
+#endif
   return RT2_OK;
 }
 
@@ -1434,6 +1478,7 @@ static void LaunchExtendT(Renderer::Impl& m, const ExtendArgs& a, uint64_t* laun
   } else if (m.split_mode) {
     SplitIO io = a.io;
     io.entry_count = a.entry_count;
+    if (io.capacity == 0) io.capacity = a.n_fixed * m.ds.n_hoisted;  // rt2_intersect sizes its own queue
     k_traverse<M, kCount, kTravWorld><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
                                                                           a.order, a.sort_min_rays, a.trav, io, m.totals, m.trav_max_steps,
                                                                           m.trav_fetch_threshold);

@@ -5,7 +5,7 @@
 //
 // Pipeline (all hand-written kernels, HBM-bound integer work; no CUB / Thrust):
 //   k_lbvh_bounds      centroid bounds (block reduction + ordered-int atomics)
-//   k_lbvh_morton      63-bit Morton code of each centroid (21 bits per axis on ONE isotropic grid), value = primitive slot
+//   k_lbvh_morton      63-bit Morton code of each centroid (21 bits per axis), value = primitive slot
 //   k_radix_*          LSD radix sort of (key, value), 8-bit digits over the bits in use: per-tile histograms, one scan, stable scatter
 //   k_lbvh_gather      leaf boxes / primitive references in sorted order
 //   k_lbvh_hierarchy   Karras 2012: one thread per internal node finds its key range and split
@@ -73,25 +73,22 @@ __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_bounds(const rt2::BuildPrim
 
 // Morton grid = mean +- 3 sigma of the centroids, clamped to their true bounds: a single far-away giant (the r = 1e5 ground
 // sphere of the stress scene) would otherwise squeeze every other primitive into a handful of cells along one axis.
-// The grid is ISOTROPIC — one cell size for all three axes, 2^21 cells along the longest one: with a cell size per axis a
-// flat scene (the stress scene is 2000 x 200 x 2000) is cut as often along its thin axis as along the long ones, and every
-// node down to the leaves keeps the 10 : 1 : 10 slab shape of the scene (measured: 48 node pairs per ray at 10 M spheres).
-// With cubic cells the high bits of the thin axis are equal for all keys, Karras' split search skips them, and the nodes
-// become cubes.  grid[0..2] = origin, grid[3] = cells per unit.
+// Every axis gets its own cell size (2^21 cells over its own extent).  An ISOTROPIC grid (one cell size for all axes, so that
+// a flat scene is not cut as often along its thin axis) was measured WORSE on the 2000 x 200 x 2000 stress scene: 35.6 vs
+// 30.0 node pairs per ray at 1 M spheres, 49.9 vs 48.0 at 10 M (profiles/r02_notes.md) — the early cuts across the thin
+// axis are what separates the rays that skim over the slab from the spheres inside it.
+// grid[0..2] = origin, grid[3..5] = cells per unit.
 constexpr int kMortonBitsPerAxis = 21;
 __global__ void k_lbvh_grid(uint32_t n, const int* __restrict__ bounds, const double* __restrict__ moments, float* __restrict__ grid) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float extent = 0.0f;
-  for (int k = 0; k < 3; k++) {
-    const double mean = moments[k] / n;
-    const double var = fmax(moments[3 + k] / n - mean * mean, 0.0);
-    const double sd = sqrt(var);
-    const float lo = fmaxf(ordered_to_float(bounds[k]), static_cast<float>(mean - 3.0 * sd));
-    const float hi = fminf(ordered_to_float(bounds[3 + k]), static_cast<float>(mean + 3.0 * sd));
-    grid[k] = lo;
-    extent = fmaxf(extent, hi - lo);
-  }
-  grid[3] = extent > 0.0f ? static_cast<float>((1u << kMortonBitsPerAxis) - 1u) / extent : 0.0f;
+  if (threadIdx.x >= 3 || blockIdx.x != 0) return;
+  const int k = threadIdx.x;
+  const double mean = moments[k] / n;
+  const double var = fmax(moments[3 + k] / n - mean * mean, 0.0);
+  const double sd = sqrt(var);
+  const float lo = fmaxf(ordered_to_float(bounds[k]), static_cast<float>(mean - 3.0 * sd));
+  const float hi = fminf(ordered_to_float(bounds[3 + k]), static_cast<float>(mean + 3.0 * sd));
+  grid[k] = lo;
+  grid[3 + k] = hi > lo ? static_cast<float>((1u << kMortonBitsPerAxis) - 1u) / (hi - lo) : 0.0f;
 }
 
 // spreads the low 21 bits of v to every third bit
@@ -113,11 +110,11 @@ __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_morton(const rt2::BuildPrim
   if (i < n) {
     const rt2::BuildPrim p = prims[i];
     uint32_t q[3];
-    const float cells = grid[3], top = static_cast<float>((1u << kMortonBitsPerAxis) - 1u);
+    const float top = static_cast<float>((1u << kMortonBitsPerAxis) - 1u);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       const float c = 0.5f * (p.bmin[k] + p.bmax[k]);
-      const float u = fminf(fmaxf((c - grid[k]) * cells, 0.0f), top);  // outliers clamp to the border cells
+      const float u = fminf(fmaxf((c - grid[k]) * grid[3 + k], 0.0f), top);  // outliers clamp to the border cells
       q[k] = static_cast<uint32_t>(u);
     }
     key = (expand_bits21(q[0]) << 2) | (expand_bits21(q[1]) << 1) | expand_bits21(q[2]);
@@ -434,7 +431,7 @@ int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, 
   char* head = take(256);
   int* bounds = reinterpret_cast<int*>(head);                // 6 ints
   double* moments = reinterpret_cast<double*>(head + 64);   // 6 doubles
-  float* grid = reinterpret_cast<float*>(head + 128);        // 4 floats
+  float* grid = reinterpret_cast<float*>(head + 128);        // 6 floats
   unsigned long long* key_or = reinterpret_cast<unsigned long long*>(head + 192);
   unsigned long long* keys_a = reinterpret_cast<unsigned long long*>(take(sz_u2));
   unsigned long long* keys_b = reinterpret_cast<unsigned long long*>(take(sz_u2));

@@ -37,6 +37,7 @@ class Renderer {
   int WaitFor(void* event);          // this renderer's stream waits for another renderer's event
   void* AccumPtr();
   void* AccumSqPtr();
+  int DebugCounters(uint64_t* out16, int* enabled);
   int TextureValue(uint32_t tex_idx, const float* points, const float* uv, size_t n, float* rgb);
   int Intersect(const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out);
   int GetStats(rt2_stats* out);

@@ -13,6 +13,28 @@
 
 namespace rt2dev {
 
+// Device-side self checks (compute-sanitizer is closed on this GPU pool, so the library carries its own): a DEBUG_CHECKS build
+// (`make DEBUG_CHECKS=1` -> libraytrace2_b200_dbg.so) verifies every data-dependent index before it is used — node, primitive,
+// material, texture, queue, entry and stack indices — counts violations per site in g_rt2_violations (never traps, so one run
+// reports all of them) and poisons every wavefront buffer with NaN patterns at allocation (an uninitialised read then shows up
+// as a NaN pixel).  tests/test_gpu_debug_checks.py runs every kernel family through it and asserts all counters are zero.
+// The shipped library compiles the checks out.
+enum {
+  kChkNode = 0, kChkSphere, kChkQuad, kChkInstance, kChkInstLeaf, kChkStack, kChkQueue, kChkEntry, kChkMaterial, kChkTexture,
+  kChkSlot, kChkBin, kChkMedium, kChkPrimRef, kChkNaN, kChkCount
+};
+#ifdef RT2_DEBUG_CHECKS
+__device__ unsigned long long g_rt2_violations[kChkCount];
+#define RT2_CHECK(cond, code)                                    \
+  do {                                                           \
+    if (!(cond)) atomicAdd(&g_rt2_violations[code], 1ull);       \
+  } while (0)
+#else
+#define RT2_CHECK(cond, code) \
+  do {                        \
+  } while (0)
+#endif
+
 struct DeviceScene {
   const float4* __restrict__ spheres;    // 2 x float4 per sphere  {c0.xyz, r} {disp.xyz, mat}
   const float4* __restrict__ quads;      // 5 x float4 per quad    {n.xyz, d} {q.xyz, mat} {u} {v} {w}
@@ -26,6 +48,8 @@ struct DeviceScene {
   const uint4* __restrict__ images;        // {texel_offset, width, height, 0} per image texture
   const float4* __restrict__ image_texels;  // linear RGBA, row 0 = top
   uint32_t n_images;
+  // element counts of the buffers above (used by the DEBUG_CHECKS build only)
+  uint32_t n_spheres, n_quads, n_materials, n_textures, n_node_pairs, n_prim_refs, n_inst_leaves;
   const uint32_t* __restrict__ prim_refs;
   const float4* __restrict__ nodes;  // 4 x float4 per node pair
   uint32_t tlas_root;        // world TLAS with the instances as singleton leaves (kTravInline)
@@ -280,6 +304,7 @@ struct SplitIO {
   uint32_t* entry_prim;            // per entry: winning primitive inside the instance (valid when it won)
   unsigned long long* inst_best;   // per ray: ordered(t) << 32 | entry index, minimum over the ray's entries
   uint32_t* entry_count;           // entries of this bounce
+  uint32_t capacity;               // entries the queue can hold (DEBUG_CHECKS)
 };
 
 // Monotone map float -> uint32 (also for negative t of caller-supplied intervals) and back.
@@ -420,6 +445,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
               // one entry: the ray in the instance's model space, bounded by its closest world-space surface
               entry_idx = pos;
               const uint2 ent = io.entries[pos];
+              RT2_CHECK(ent.y < S.n_instances, kChkInstance);
               ray_idx = ent.x;
               const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
               time = wo.w;
@@ -462,6 +488,8 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
     while (true) {
       // phase 1: interior nodes (at most max_steps per round, so that lanes holding a leaf do not wait for a long descent)
       for (int step = 0; step < max_steps && active && !(cur & kLeafFlag); step++) {
+        RT2_CHECK(cur < S.n_node_pairs, kChkNode);
+        RT2_CHECK(sp >= 2 && sp <= kStackSize, kChkStack);
         const float4* np = S.nodes + static_cast<size_t>(cur) * 4;
         // (one 256-bit load per node — LDG.E.256 on sm_100 — measured 4 % SLOWER than these four 128-bit loads; r02 notes)
         const float4 a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
@@ -514,8 +542,14 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         const uint32_t count = direct ? 1u : (((cur >> 26) & 0xFu) + 1u);
         bool entered = false;
         for (uint32_t i = 0; i < count; i++) {
+          RT2_CHECK(direct || first + i < S.n_prim_refs, kChkPrimRef);
           const uint32_t ref = direct ? (cur & 0x3FFFFFFFu) : __ldg(S.prim_refs + first + i);
           const uint32_t type = RT2_PRIM_TYPE(ref), idx = RT2_PRIM_INDEX(ref);
+          RT2_CHECK(type != RT2_PRIM_SPHERE || idx < S.n_spheres, kChkSphere);
+          RT2_CHECK(type != RT2_PRIM_QUAD || idx < S.n_quads, kChkQuad);
+          RT2_CHECK(type != RT2_PRIM_INSTANCE || kMode != kTravUnified || idx < S.n_inst_leaves, kChkInstLeaf);
+          RT2_CHECK(type != RT2_PRIM_INSTANCE || kMode != kTravInline || idx < S.n_instances, kChkInstance);
+          RT2_CHECK(type <= RT2_PRIM_INSTANCE && (type != RT2_PRIM_INSTANCE || kMode == kTravUnified || kMode == kTravInline), kChkPrimRef);
           if (type == RT2_PRIM_SPHERE) {
             if (kCount) cnt.spheres++;
             float t;
@@ -535,6 +569,8 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
           } else if (kMode == kTravUnified) {
             // instanced leaf: primitive il.x of instance il.y, tested in the instance's model space (Transform.cpp:13-20,75-88)
             const uint2 il = __ldg(S.inst_leaves + idx);
+            RT2_CHECK(il.y < S.n_instances, kChkInstance);
+            RT2_CHECK(RT2_PRIM_TYPE(il.x) == RT2_PRIM_SPHERE ? RT2_PRIM_INDEX(il.x) < S.n_spheres : RT2_PRIM_INDEX(il.x) < S.n_quads, kChkInstLeaf);
             float* ms = ms_cache + threadIdx.x;
             if (cur_inst != static_cast<int32_t>(il.y)) {
               if (kCount) cnt.instances++;
@@ -606,6 +642,7 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
               if (static_cast<int>(lane) == leader) base = atomicAdd(io.entry_count, __popc(tm));
               base = __shfl_sync(kFull, base, leader);
               if (touch) {
+                RT2_CHECK(base + __popc(tm & ((1u << lane) - 1u)) < io.capacity, kChkEntry);
                 io.entries[base + __popc(tm & ((1u << lane) - 1u))] = make_uint2(ray_idx, j);
                 has_entry = true;
                 if (kCount) cnt.instances++;
@@ -882,6 +919,7 @@ __device__ __forceinline__ void finish_record(const DeviceScene& S, F3 wo, F3 wd
   out.instance = best.instance;
   out.u = out.v = 0.0f;
   if (medium_hit >= 0) {
+    RT2_CHECK(static_cast<uint32_t>(medium_hit) < S.n_media, kChkMedium);
     const uint4 m0 = __ldg(S.media + 2 * medium_hit), m1 = __ldg(S.media + 2 * medium_hit + 1);
     RaySpace rs{wo, wd};
     if (!kSimple) rs = to_chain_space<M>(S, m1.x, m1.y, rs);
@@ -914,6 +952,8 @@ __device__ __forceinline__ void finish_record(const DeviceScene& S, F3 wo, F3 wd
     rs = to_chain_space<M>(S, chain_first, chain_len, rs);
   }
   const uint32_t idx = RT2_PRIM_INDEX(best.prim);
+  RT2_CHECK(RT2_PRIM_TYPE(best.prim) == RT2_PRIM_SPHERE ? idx < S.n_spheres : (RT2_PRIM_TYPE(best.prim) == RT2_PRIM_QUAD && idx < S.n_quads), kChkPrimRef);
+  RT2_CHECK(best.instance < static_cast<int32_t>(S.n_instances), kChkInstance);
   F3 p = ray_at<M>(rs.o, rs.d, best.t);
   F3 outward;
   uint32_t mat;

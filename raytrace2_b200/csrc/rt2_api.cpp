@@ -266,6 +266,10 @@ int rt2_get_stats(rt2_renderer* r, rt2_stats* out) {
   if (!out) return Fail(RT2_ERR_INVALID_ARG, "null argument");
   RT2_FORWARD(r->impl.GetStats(out))
 }
+int rt2_debug_counters(rt2_renderer* r, uint64_t* counters, int* enabled) {
+  if (!counters || !enabled) return Fail(RT2_ERR_INVALID_ARG, "null argument");
+  RT2_FIRST_RC(r->impl.First().DebugCounters(counters, enabled))
+}
 int rt2_set_profiling(rt2_renderer* r, int enabled) {
   if (!r) return Fail(RT2_ERR_INVALID_ARG, "null renderer");
   r->impl.SetProfiling(enabled != 0);

@@ -347,6 +347,15 @@ class RayTracer:
     def set_profiling(self, enabled: bool) -> None:
         check(self._lib.rt2_set_profiling(self._h, int(enabled)))
 
+    def debug_counters(self):
+        """(enabled, {check: violations}) of the device-side self checks (a `make DEBUG_CHECKS=1` build; else enabled is False)."""
+        names = ["node", "sphere", "quad", "instance", "inst_leaf", "stack", "queue", "entry", "material", "texture", "slot", "bin",
+                 "medium", "prim_ref", "nan", "reserved"]
+        buf = (C.c_uint64 * 16)()
+        en = C.c_int(0)
+        check(self._lib.rt2_debug_counters(self._h, buf, C.byref(en)))
+        return bool(en.value), {n: int(v) for n, v in zip(names, buf)}
+
     def stats(self) -> dict:
         st = _capi.Stats()
         check(self._lib.rt2_get_stats(self._h, C.byref(st)))

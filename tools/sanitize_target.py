@@ -22,6 +22,19 @@ def scene(name):
     return rt.Scene.load(os.path.join(ROOT, "data", name + ".json"), perlin_seed=3)
 
 
+CHECKS = {"enabled": None, "violations": {}, "nan_pixels": 0}
+
+
+def collect(tr, img=None):
+    """Fold the device-side self-check counters of `tr` (DEBUG_CHECKS build) and NaN pixels of `img` into CHECKS."""
+    en, c = tr.debug_counters()
+    CHECKS["enabled"] = en
+    for k, v in c.items():
+        CHECKS["violations"][k] = max(CHECKS["violations"].get(k, 0), v)  # the counters are per process, cumulative
+    if img is not None:
+        CHECKS["nan_pixels"] += int(np.isnan(img).sum())
+
+
 def main():
     n_dev = rt.load_library().rt2_device_count()
     done = []
@@ -45,7 +58,7 @@ def main():
         tr.texture_value(0, np.random.default_rng(0).uniform(-5, 5, (64, 3)).astype(np.float32))
         tr.OnResize((40, 24))
         tr.Update(1)
-        tr.NonConvertedPixels()
+        collect(tr, tr.NonConvertedPixels())
         done.append(f"book2/{label}")
         del tr
     for name, flags in [("cornell_original_test", 0), ("cornell_original_test", rt.RT2_FLAG_NO_FLAT_EXTEND),
@@ -56,7 +69,7 @@ def main():
         oo, dd, tt = fixed_rays(sc, 1500, seed=2)
         tr.intersect(oo, dd, tt)
         tr.Update(3)
-        tr.NonConvertedPixels()
+        collect(tr, tr.NonConvertedPixels())
         handle = tr.accum_ipc_handle()
         tr.resolve_peers([handle], 0, 3)
         done.append(f"{name}/{flags}")
@@ -65,17 +78,19 @@ def main():
     for flags in (rt.RT2_FLAG_GPU_LBVH, rt.RT2_FLAG_GPU_LBVH | rt.RT2_FLAG_WIDE_BVH):
         tr = rt.RayTracer(syn, num_samples=2, max_depth=8, flags=flags, frames_per_batch=2)
         tr.Update(2)
-        tr.NonConvertedPixels()
+        collect(tr, tr.NonConvertedPixels())
         done.append(f"synthetic/{flags}")
         del tr
     if n_dev >= 2:
         tr = rt.RayTracer(book2, num_samples=8, max_depth=10, seed=2, dims=(48, 48), frames_per_batch=2, n_gpus=2, flags=rt.RT2_FLAG_MOMENTS)
         tr.Update(5)
-        tr.NonConvertedPixels()
+        collect(tr, tr.NonConvertedPixels())
         tr.Pixels()
         tr.read_accum(moments=True)
         done.append("multi-gpu handle")
     print("sanitize_target OK:", ", ".join(done))
+    import json
+    print("DEBUG_CHECKS " + json.dumps(CHECKS))
 
 
 if __name__ == "__main__":
