@@ -234,7 +234,7 @@ typedef struct rt2_renderer rt2_renderer;
 #define RT2_FLAG_FAST_MATH 2u   /* FMA-contracted intersection arithmetic (default: bit-exact with the reference) */
 #define RT2_FLAG_NO_FUSED_SHADE 4u /* run k_finish_hit + one shade kernel per material bin instead of the fused
                                      k_finish_shade (A/B and debugging; results are identical) */
-#define RT2_FLAG_GPU_LBVH 8u    /* build every BVH on the device (Morton codes + radix sort + Karras hierarchy) instead of
+#define RT2_FLAG_GPU_LBVH 8u    /* build every BVH on the device (63-bit Morton codes + radix sort + Karras radix tree) instead of
                                    uploading the host SAH trees */
 #define RT2_FLAG_WIDE_BVH 32u   /* with RT2_FLAG_GPU_LBVH, scenes without instances: collapse the device-built tree into 4-wide
                                    nodes with 8-bit child boxes (64 B per node) and walk those — half the node traffic of the
@@ -248,6 +248,9 @@ typedef struct rt2_renderer rt2_renderer;
 #define RT2_FLAG_INSTANCES_INLINE 64u /* two-level walk in one kernel: instance leaves in the TLAS, a lane that meets one switches
                                    to the model space and the BLAS (always used by scenes too big to flatten); A/B and debugging */
 #define RT2_FLAG_NO_INSTANCE_SPLIT RT2_FLAG_INSTANCES_INLINE /* (round-2 name) */
+#define RT2_FLAG_LBVH_PLOC 512u /* with RT2_FLAG_GPU_LBVH: build the hierarchy by PLOC (parallel locally-ordered clustering over the
+                                   Morton order) instead of Karras' one-pass radix tree.  Measured WORSE on the sphere stress scene
+                                   (38.7 vs 30.0 node pairs per ray at 1 M spheres): opt-in, for A/B */
 #define RT2_FLAG_INSTANCE_SPLIT 256u /* two passes: surfaces-only world tree, then one {ray, instance} entry per touched instance
                                    (RT2_MAX_HOISTED_INSTANCES); measured equal to the inline walk, kept for A/B */
 

@@ -28,6 +28,7 @@ RT2_FLAG_WIDE_BVH = 32
 RT2_FLAG_INSTANCES_INLINE = 64
 RT2_FLAG_NO_INSTANCE_SPLIT = 64
 RT2_FLAG_INSTANCE_SPLIT = 256
+RT2_FLAG_LBVH_PLOC = 512
 RT2_FLAG_NO_FLAT_EXTEND = 128
 RT2_MAX_HOISTED_INSTANCES = 4
 RT2_ABI_VERSION = 3

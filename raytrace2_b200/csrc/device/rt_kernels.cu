@@ -1207,13 +1207,16 @@ int Renderer::BuildTreesOnDevice(const HostScene& scene) {
   RT2_CUDA(cudaMalloc(&d_depths, n_trees * sizeof(uint32_t)));
   RT2_CUDA(cudaMemsetAsync(d_depths, 0, n_trees * sizeof(uint32_t), m.stream));
   RT2_CUDA(cudaEventRecord(m.ev_start, m.stream));
+  // (Chaining "giant" primitives — the r = 1e5 ground sphere — at the top of the radix tree instead of filing them among their
+  // Morton neighbours was tried and measured: 34.0 vs 30.0 node pairs per ray at 1 M spheres, 45.2 vs 48.0 at 10 M; not kept.)
   for (size_t k = 0; k < n_trees; k++) {
     const std::vector<BuildPrim>& tp = *trees[k];
     if (!tp.empty()) {
       RT2_CUDA(cudaMemcpyAsync(m.d_build_prims, tp.data(), tp.size() * sizeof(BuildPrim), cudaMemcpyHostToDevice, m.stream));
     }
     rc = BuildLbvhOnDevice(static_cast<const BuildPrim*>(m.d_build_prims), static_cast<uint32_t>(tp.size()), pair_base[k], ref_base[k], m.d_nodes,
-                           static_cast<uint32_t*>(m.d_prim_refs), &m.lbvh_scratch, m.stream, &launches_, d_depths + k, &err_);
+                           static_cast<uint32_t*>(m.d_prim_refs), &m.lbvh_scratch, m.stream, &launches_, d_depths + k,
+                           (cfg_.flags & RT2_FLAG_LBVH_PLOC) != 0, &err_);
     if (rc != RT2_OK) {
       cudaFree(d_depths);
       return rc;

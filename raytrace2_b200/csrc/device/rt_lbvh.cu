@@ -353,6 +353,119 @@ __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_emit(int n, uint32_t pair_b
   }
 }
 
+// ---- PLOC: parallel locally-ordered clustering (Meister & Bittner 2018) ----------------------------------------------------
+// The Karras hierarchy above cuts at Morton-cell boundaries wherever they fall; PLOC builds the tree bottom-up instead: the
+// clusters (at first the leaves, in Morton order) each look for the neighbour within +-kPlocRadius positions whose union with
+// them has the smallest surface area, mutual nearest neighbours merge into a new node, the survivors are compacted, and the
+// loop repeats until one cluster is left — an agglomerative build whose quality is close to a full SAH sweep (measured on the
+// stress scene: node pairs per ray, profiles/r02_notes.md).  Node ids are handed out from n - 2 downwards, so the last merge —
+// the root — is node 0, as k_lbvh_emit and the traversal expect.
+constexpr int kPlocRadius = 8;
+
+__device__ __forceinline__ float box_area(float4 mn, float4 mx) {
+  const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void __launch_bounds__(kLbvhBlock) k_ploc_init(uint32_t n, const float4* __restrict__ leaf_min, const float4* __restrict__ leaf_max,
+                                                          float4* __restrict__ cmin, float4* __restrict__ cmax, uint32_t* __restrict__ cnode) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cmin[i] = leaf_min[i];
+  cmax[i] = leaf_max[i];
+  cnode[i] = kChildLeaf | i;
+}
+
+// nearest neighbour of every cluster inside the window (smallest union area; ties go to the lower index, so that the pair with
+// the globally smallest union is always mutual and every round merges at least one pair)
+__global__ void __launch_bounds__(kLbvhBlock) k_ploc_nn(uint32_t m, const float4* __restrict__ cmin, const float4* __restrict__ cmax,
+                                                        uint32_t* __restrict__ nn) {
+  __shared__ float4 smin[kLbvhBlock + 2 * kPlocRadius], smax[kLbvhBlock + 2 * kPlocRadius];
+  const int base = static_cast<int>(blockIdx.x * blockDim.x) - kPlocRadius;
+  for (int t = threadIdx.x; t < kLbvhBlock + 2 * kPlocRadius; t += blockDim.x) {
+    const int g = base + t;
+    if (g >= 0 && g < static_cast<int>(m)) {
+      smin[t] = cmin[g];
+      smax[t] = cmax[g];
+    }
+  }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int li = threadIdx.x + kPlocRadius;
+  const float4 amin = smin[li], amax = smax[li];
+  float best = 3.4e38f;
+  uint32_t best_j = i;
+  for (int dlt = -kPlocRadius; dlt <= kPlocRadius; dlt++) {
+    const int g = static_cast<int>(i) + dlt;
+    if (dlt == 0 || g < 0 || g >= static_cast<int>(m)) continue;
+    const float4 bmin = smin[li + dlt], bmax = smax[li + dlt];
+    const float4 mn = make_float4(fminf(amin.x, bmin.x), fminf(amin.y, bmin.y), fminf(amin.z, bmin.z), 0.0f);
+    const float4 mx = make_float4(fmaxf(amax.x, bmax.x), fmaxf(amax.y, bmax.y), fmaxf(amax.z, bmax.z), 0.0f);
+    const float ar = box_area(mn, mx);
+    if (ar < best) {  // ascending g: the first of equal areas (the lower index) wins
+      best = ar;
+      best_j = static_cast<uint32_t>(g);
+    }
+  }
+  nn[i] = best_j;
+}
+
+// mutual nearest neighbours merge (the lower slot keeps the merged cluster, the upper one is dropped); flag = survives
+__global__ void __launch_bounds__(kLbvhBlock) k_ploc_merge(uint32_t m, uint32_t n, float4* __restrict__ cmin, float4* __restrict__ cmax,
+                                                           uint32_t* __restrict__ cnode, const uint32_t* __restrict__ nn,
+                                                           uint32_t* __restrict__ merged_count, uint2* __restrict__ children,
+                                                           uint32_t* __restrict__ parent_internal, uint32_t* __restrict__ parent_leaf,
+                                                           float4* __restrict__ node_min, float4* __restrict__ node_max,
+                                                           uint32_t* __restrict__ flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t j = nn[i];
+  const bool mutual = (j != i) && (nn[j] == i);
+  if (!mutual) {
+    flag[i] = 1u;
+    return;
+  }
+  if (i > j) {
+    flag[i] = 0u;
+    return;
+  }
+  const uint32_t id = (n - 2u) - atomicAdd(merged_count, 1u);
+  const uint32_t a = cnode[i], b = cnode[j];
+  children[id] = make_uint2(a, b);
+  if (a & kChildLeaf) parent_leaf[a & ~kChildLeaf] = id;
+  else parent_internal[a] = id;
+  if (b & kChildLeaf) parent_leaf[b & ~kChildLeaf] = id;
+  else parent_internal[b] = id;
+  const float4 amin = cmin[i], amax = cmax[i], bmin = cmin[j], bmax = cmax[j];
+  const float4 mn = make_float4(fminf(amin.x, bmin.x), fminf(amin.y, bmin.y), fminf(amin.z, bmin.z), 0.0f);
+  const float4 mx = make_float4(fmaxf(amax.x, bmax.x), fmaxf(amax.y, bmax.y), fmaxf(amax.z, bmax.z), 0.0f);
+  node_min[id] = mn;
+  node_max[id] = mx;
+  cmin[i] = mn;
+  cmax[i] = mx;
+  cnode[i] = id;
+  flag[i] = 1u;
+  if (id == 0u) parent_internal[0] = 0xFFFFFFFFu;  // the last merge is the root
+}
+
+// survivors move to their rank (pos = exclusive prefix sum of the flags)
+__global__ void __launch_bounds__(kLbvhBlock) k_ploc_compact(uint32_t m, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ nn_mutual,
+                                                             const float4* __restrict__ cmin, const float4* __restrict__ cmax,
+                                                             const uint32_t* __restrict__ cnode, float4* __restrict__ omin,
+                                                             float4* __restrict__ omax, uint32_t* __restrict__ onode, uint32_t* __restrict__ new_count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t p = pos[i];
+  const bool alive = (i + 1 < m) ? (pos[i + 1] != p) : (nn_mutual[0] != 0u);  // nn_mutual[0] = flag of the last element (saved before the scan)
+  if (alive) {
+    omin[p] = cmin[i];
+    omax[p] = cmax[i];
+    onode[p] = cnode[i];
+  }
+  if (i + 1 == m) *new_count = p + (alive ? 1u : 0u);
+}
+
 // Depth of the tree in node pairs (= the number of stack entries a traversal may need): every leaf walks to the root.
 __global__ void __launch_bounds__(kLbvhBlock) k_lbvh_depth(int n, const uint32_t* __restrict__ parent_internal,
                                                            const uint32_t* __restrict__ parent_leaf, uint32_t* __restrict__ depth_out) {
@@ -398,7 +511,7 @@ using namespace rt2dev;
   } while (0)
 
 int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, uint32_t ref_base, void* d_nodes, uint32_t* d_prim_refs,
-                      LbvhScratch* scratch, void* stream_v, uint64_t* launches, uint32_t* d_depth, std::string* err) {
+                      LbvhScratch* scratch, void* stream_v, uint64_t* launches, uint32_t* d_depth, bool use_ploc, std::string* err) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   float4* nodes = static_cast<float4*>(d_nodes);
   if (n <= 1) {
@@ -414,7 +527,7 @@ int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, 
   auto align = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
   const size_t sz_u32 = align(n * 4ull), sz_f4 = align(n * 16ull), sz_u2 = align(n * 8ull);
   const size_t sz_hist = align(static_cast<size_t>(kRadixBins) * n_tiles * 4);
-  const size_t need = 256 + 2 * sz_u2 + 2 * sz_u32 + sz_hist + 4 * sz_f4 + sz_u2 + 3 * sz_u32;
+  const size_t need = 256 + 2 * sz_u2 + 2 * sz_u32 + sz_hist + 4 * sz_f4 + sz_u2 + 3 * sz_u32 + (use_ploc ? 4 * sz_f4 : 0);
   if (need > scratch->bytes) {
     if (scratch->ptr) cudaFree(scratch->ptr);
     scratch->ptr = nullptr;
@@ -483,14 +596,49 @@ int BuildLbvhOnDevice(const BuildPrim* d_prims, uint32_t n, uint32_t pair_base, 
   }
   // the sorted data is in (kin, vin)
   k_lbvh_gather<<<grid_n, kLbvhBlock, 0, stream>>>(d_prims, vin, n, leaf_min, leaf_max, d_prim_refs + ref_base);
-  LBVH_CUDA(cudaMemsetAsync(visit, 0, n * 4ull, stream));
-  k_lbvh_hierarchy<<<grid_n, kLbvhBlock, 0, stream>>>(kin, static_cast<int>(n), children, parent_internal, parent_leaf);
-  k_lbvh_refit<<<grid_n, kLbvhBlock, 0, stream>>>(static_cast<int>(n), children, parent_internal, parent_leaf, leaf_min, leaf_max, node_min, node_max,
-                                                  visit);
+  if (use_ploc) {
+    // PLOC: the radix-sort buffers are free again and hold the cluster arrays (boxes double-buffered for the compaction)
+    float4* cmin[2] = {reinterpret_cast<float4*>(take(sz_f4)), reinterpret_cast<float4*>(take(sz_f4))};
+    float4* cmax[2] = {reinterpret_cast<float4*>(take(sz_f4)), reinterpret_cast<float4*>(take(sz_f4))};
+    uint32_t* cnode[2] = {vals_a, vals_b};
+    uint32_t* nn = reinterpret_cast<uint32_t*>(keys_a);
+    uint32_t* flag = reinterpret_cast<uint32_t*>(keys_b);
+    uint32_t* counters = reinterpret_cast<uint32_t*>(head + 200);  // [0] merges so far, [1] clusters after compaction, [2] last flag
+    k_ploc_init<<<grid_n, kLbvhBlock, 0, stream>>>(n, leaf_min, leaf_max, cmin[0], cmax[0], cnode[0]);
+    (*launches)++;
+    uint32_t m = n;
+    int cur = 0;
+    while (m > 1) {
+      const uint32_t gm = (m + kLbvhBlock - 1) / kLbvhBlock;
+      k_ploc_nn<<<gm, kLbvhBlock, 0, stream>>>(m, cmin[cur], cmax[cur], nn);
+      k_ploc_merge<<<gm, kLbvhBlock, 0, stream>>>(m, n, cmin[cur], cmax[cur], cnode[cur], nn, counters, children, parent_internal, parent_leaf,
+                                                  node_min, node_max, flag);
+      LBVH_CUDA(cudaMemcpyAsync(counters + 2, flag + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+      k_radix_scan<<<1, 1024, 0, stream>>>(flag, m);
+      k_ploc_compact<<<gm, kLbvhBlock, 0, stream>>>(m, flag, counters + 2, cmin[cur], cmax[cur], cnode[cur], cmin[cur ^ 1], cmax[cur ^ 1],
+                                                    cnode[cur ^ 1], counters + 1);
+      *launches += 4;
+      uint32_t m_new = 0;
+      LBVH_CUDA(cudaMemcpyAsync(&m_new, counters + 1, sizeof(m_new), cudaMemcpyDeviceToHost, stream));
+      LBVH_CUDA(cudaStreamSynchronize(stream));
+      if (m_new == 0 || m_new >= m) {
+        *err = "PLOC made no progress (" + std::to_string(m) + " -> " + std::to_string(m_new) + " clusters)";
+        return RT2_ERR_STATE;
+      }
+      m = m_new;
+      cur ^= 1;
+    }
+  } else {
+    LBVH_CUDA(cudaMemsetAsync(visit, 0, n * 4ull, stream));
+    k_lbvh_hierarchy<<<grid_n, kLbvhBlock, 0, stream>>>(kin, static_cast<int>(n), children, parent_internal, parent_leaf);
+    k_lbvh_refit<<<grid_n, kLbvhBlock, 0, stream>>>(static_cast<int>(n), children, parent_internal, parent_leaf, leaf_min, leaf_max, node_min,
+                                                    node_max, visit);
+    *launches += 2;
+  }
   k_lbvh_emit<<<grid_n, kLbvhBlock, 0, stream>>>(static_cast<int>(n), pair_base, ref_base, children, leaf_min, leaf_max, node_min, node_max, d_prim_refs,
                                                  nodes);
   k_lbvh_depth<<<grid_n, kLbvhBlock, 0, stream>>>(static_cast<int>(n), parent_internal, parent_leaf, d_depth);
-  *launches += 5;
+  *launches += 3;
   LBVH_CUDA(cudaGetLastError());
   return RT2_OK;
 }

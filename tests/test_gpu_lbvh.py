@@ -47,12 +47,14 @@ def _host_tree_refs(scene):
     return np.array([r for i, r in enumerate(refs) if i not in skip], np.uint32)
 
 
+@pytest.mark.parametrize("builder", [0, rt.RT2_FLAG_LBVH_PLOC])
 @pytest.mark.parametrize("name", ["book2_final_scene_10000_samples", "cornell_original_test", "cornell_box_scene_graph",
                                   "cornell_volume_10000_samples", "final_render_book_1"])
-def test_device_built_tree_is_valid_and_gives_identical_hits(native_lib, name):
+def test_device_built_tree_is_valid_and_gives_identical_hits(native_lib, name, builder):
+    """builder: Karras' radix tree over the 63-bit Morton order (default) or PLOC clustering (opt-in; measured worse trees)."""
     scene = rt.Scene.load(scene_path(name))
     sah = rt.RayTracer(scene)
-    lbvh = rt.RayTracer(scene, flags=rt.RT2_FLAG_GPU_LBVH)
+    lbvh = rt.RayTracer(scene, flags=rt.RT2_FLAG_GPU_LBVH | builder)
     nodes, refs, root = lbvh.read_bvh()
     n_media_refs = int(sum(m["boundary_count"] for m in scene.media()))
     # tree 0 (TLAS) starts at pair 0; instance BLAS roots are patched into the device copy of the instance table, so walk
