@@ -372,6 +372,9 @@ int rt2_texture_value(rt2_renderer* r, uint32_t tex_idx, const float* points, co
 int rt2_read_bvh(rt2_renderer* r, rt2_bvh_node* nodes, size_t max_nodes, uint32_t* prim_refs, size_t max_refs, uint32_t* n_pairs,
                  uint32_t* n_refs, uint32_t* tlas_root);
 int rt2_get_stats(rt2_renderer* r, rt2_stats* out);
+/* Ray-queue sizes of the most recent wavefront batch on the first GPU: out[b] = rays traced at bounce b (b < max_bounces);
+ * *n_bounces = max_depth.  For per-bounce analysis and for turning an ncu capture of one launch into bytes per ray. */
+int rt2_read_queue_sizes(rt2_renderer* r, uint32_t* out, uint32_t max_bounces, uint32_t* n_bounces);
 /* Device-side self checks.  compute-sanitizer is not available on every GPU pool, so a `make DEBUG_CHECKS=1` build of this
  * library (libraytrace2_b200_dbg.so) verifies every data-dependent index in the kernels (node, primitive, material, queue,
  * entry, stack ...) and counts violations per kind; it also poisons the wavefront buffers with NaN patterns at allocation.

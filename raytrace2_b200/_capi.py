@@ -167,6 +167,7 @@ PROTOTYPES = {
     "rt2_read_bvh": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rt2_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "rt2_debug_counters": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    "rt2_read_queue_sizes": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "rt2_set_profiling": (C.c_int, [_P, C.c_int]),
     "rt2_stream": (C.c_int, [_P, C.POINTER(_P)]),
     "rt2_write_image": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_char_p, C.c_int]),

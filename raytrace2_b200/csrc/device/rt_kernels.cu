@@ -276,6 +276,18 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) k_finish_shade(const Device
   const uint32_t n_tiles = (n + kTile - 1) / kTile;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {  // block-uniform trip count
     const uint32_t i = tile * kTile + threadIdx.x;
+    {
+      // the block's next tile: pull its four input streams into L2 now (each warp stalls once per tile on these loads —
+      // 12 % of the kernel's stall samples — and a DRAM miss costs twice an L2 hit; measured: long_scoreboard 3.45 -> 1.98
+      // per issue, kernel -8 %)
+      const uint32_t nx = i + gridDim.x * kTile;
+      if (nx < n && (threadIdx.x & 7u) == 0u) {  // one request per 128-byte line of 8 float4
+        prefetch_l2(ray_o + nx);
+        prefetch_l2(ray_d + nx);
+        prefetch_l2(trav + nx);
+        prefetch_l2(state + nx);
+      }
+    }
     bool emit = false;
     int cls = 0;
     float4 no = make_float4(0, 0, 0, 0), nd = make_float4(0, 0, 0, 0), ns = make_float4(0, 0, 0, 0);
@@ -355,7 +367,9 @@ __global__ void __launch_bounds__(kTile, kMinBlocks) k_finish_shade(const Device
     // Append the tile's scattered rays to the next queue with ONE atomic per tile, grouped by material class inside the
     // tile's slice: runs of the next queue come from neighbouring pixels / queue positions and share a material, so the
     // warps of the next bounce start from similar places with similar direction distributions (a global stable
-    // compaction by chained scan and plain per-warp atomics were both measured slower, profiles/r01_notes.md).
+    // compaction by chained scan and plain per-warp atomics were both measured slower, profiles/r01_notes.md; staging the
+    // tile in shared memory and flushing it one tile later, with the atomic's round trip hidden under the next tile's shading,
+    // measured exactly the same: the two barriers cost what the slowest warp of the tile costs, profiles/r02_notes.md).
     uint32_t(*off)[kWarps] = s_off[parity];
     unsigned my_mask = 0;
 #pragma unroll
@@ -1411,6 +1425,21 @@ int Renderer::AllocState() {
   RT2_CUDA(cudaMemset(m.mean_rgb, 0xFF, P * 3 * sizeof(float)));
 #endif
   if (m.split_mode) return AllocSplitState();
+  return RT2_OK;
+}
+
+// Ray-queue sizes of the most recent wavefront batch, one per bounce (tools: per-bounce analysis, ncu bytes-per-ray).
+int Renderer::QueueSizes(uint32_t* out, uint32_t max_bounces, uint32_t* n_bounces) {
+  Impl& m = *impl_;
+  RT2_CUDA(cudaSetDevice(cfg_.device));
+  if (!state_ok_) return NoState();
+  int rc = Synchronize();
+  if (rc != RT2_OK) return rc;
+  const uint32_t depth = static_cast<uint32_t>(cfg_.max_depth);
+  std::vector<uint32_t> ctr(static_cast<size_t>(depth) * kCounterStride);
+  RT2_CUDA(cudaMemcpy(ctr.data(), m.counters, ctr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  *n_bounces = depth;
+  for (uint32_t b = 0; b < depth && b < max_bounces; b++) out[b] = ctr[static_cast<size_t>(b) * kCounterStride];
   return RT2_OK;
 }
 

@@ -38,6 +38,7 @@ class Renderer {
   void* AccumPtr();
   void* AccumSqPtr();
   int DebugCounters(uint64_t* out16, int* enabled);
+  int QueueSizes(uint32_t* out, uint32_t max_bounces, uint32_t* n_bounces);
   int TextureValue(uint32_t tex_idx, const float* points, const float* uv, size_t n, float* rgb);
   int Intersect(const float* rays, size_t n, float tmin, float tmax, int skip_media, rt2_hit* out);
   int GetStats(rt2_stats* out);

@@ -519,7 +519,9 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         const bool both = h0 && h1, any = h0 || h1;
         const bool swap = both && (near1 < near0);
         const uint32_t near_child = (h0 && !swap) ? e0 : e1;
-        st_store(sp, swap ? e0 : e1);
+        const uint32_t far_child = swap ? e0 : e1;
+        st_store(sp, far_child);
+        // (prefetching the far child's node pair into L1 here, for the later pop: measured 5 931 vs 6 030 Mrays/s — dropped)
         if (kMode == kTravInline) {
           if (any) {
             cur = near_child;

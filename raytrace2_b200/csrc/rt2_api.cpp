@@ -266,6 +266,10 @@ int rt2_get_stats(rt2_renderer* r, rt2_stats* out) {
   if (!out) return Fail(RT2_ERR_INVALID_ARG, "null argument");
   RT2_FORWARD(r->impl.GetStats(out))
 }
+int rt2_read_queue_sizes(rt2_renderer* r, uint32_t* out, uint32_t max_bounces, uint32_t* n_bounces) {
+  if (!out || !n_bounces) return Fail(RT2_ERR_INVALID_ARG, "null argument");
+  RT2_FIRST_RC(r->impl.First().QueueSizes(out, max_bounces, n_bounces))
+}
 int rt2_debug_counters(rt2_renderer* r, uint64_t* counters, int* enabled) {
   if (!counters || !enabled) return Fail(RT2_ERR_INVALID_ARG, "null argument");
   RT2_FIRST_RC(r->impl.First().DebugCounters(counters, enabled))

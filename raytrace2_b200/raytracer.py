@@ -347,6 +347,13 @@ class RayTracer:
     def set_profiling(self, enabled: bool) -> None:
         check(self._lib.rt2_set_profiling(self._h, int(enabled)))
 
+    def queue_sizes(self) -> np.ndarray:
+        """Rays traced at every bounce of the most recent wavefront batch (first GPU)."""
+        out = np.zeros(max(self.max_depth, 1), np.uint32)
+        n = C.c_uint32(0)
+        check(self._lib.rt2_read_queue_sizes(self._h, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
+        return out[:n.value]
+
     def debug_counters(self):
         """(enabled, {check: violations}) of the device-side self checks (a `make DEBUG_CHECKS=1` build; else enabled is False)."""
         names = ["node", "sphere", "quad", "instance", "inst_leaf", "stack", "queue", "entry", "material", "texture", "slot", "bin",
