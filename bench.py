@@ -283,7 +283,8 @@ def time_config(rt, torch, D, args, name, dims, spp_step, steps=2, warmup=1):
     (rays, paths), (ms_all,) = D.sum_max([st1["rays"] - st0["rays"], st1["paths"] - st0["paths"]], [ms])
     row = {"workload": f"{label} {W}x{H}, {spp_step} spp per step per GPU", "Mrays_per_s": rays / (ms_all * 1e-3) * 1e-6,
            "paths_per_s": paths / (ms_all * 1e-3), "rays_per_path": rays / max(paths, 1), "ms_per_step": ms_all / steps,
-           "bvh_build_ms": st1["gpu_ms_bvh_build"], "instance_split": st1["instance_split"], "stack_overflows": st1["stack_overflows"]}
+           "bvh_build_ms": st1["gpu_ms_bvh_build"], "instance_mode": st1["instance_mode"], "max_stack_need": st1["max_stack_need"],
+           "stack_overflows": st1["stack_overflows"]}
     del tracer, scene
     return row
 
@@ -380,10 +381,13 @@ def run_ours(args):
     prof_total = ext_ms + inst_ms + ps["gpu_ms_shade"] + ps["gpu_ms_other"] + ps["gpu_ms_finish"] + ps["gpu_ms_sort"]
     n_trav_launches = max(1, prof_steps * args.max_depth)  # one world-pass launch per bounce and batch
     rays_per_launch = ps["rays"] / n_trav_launches
+    mode = ps.get("instance_mode", 0)
     if ps["box_pair_tests"] == 0:
         kernel_name = "k_traverse_flat"
-    elif ps["instance_split"]:
+    elif mode == 2:
         kernel_name = "k_traverse<kTravWorld> (+ k_traverse<kTravInst>)"
+    elif mode == 3:
+        kernel_name = "k_traverse<kTravUnified>"
     else:
         kernel_name = "k_traverse<kTravInline>"
     trav_ms = ext_ms + inst_ms  # both passes of the extend stage
@@ -410,10 +414,11 @@ def run_ours(args):
                 "flop_per_ray": flops / max(ps["rays"], 1), "per_ray": per_ray,
                 "avg_launch_ms": trav_ms / n_trav_launches, "rays_per_launch": rays_per_launch,
                 "share_of_step": trav_ms / prof_total if prof_total > 0 else None,
-                "note": "the extend stage is instruction-issue bound under SIMT divergence (the scene lives in L1/L2), so the binding "
-                        "roofline is FP32 / issue: credited flops per SURVEY Appendix C (30 / AABB test, 30 / sphere, 57 / quad, "
-                        "42 / instance entry) of the work done by ACTIVE lanes (device counters); 0 for the flat extend kernel, "
-                        "which has no counters"}
+                "note": "the extend stage runs out of L1: ncu shows l1tex throughput at 88 % of peak, 58-65 % of issue slots busy at 13-17 of "
+                        "32 lanes and long-scoreboard as the top stall (profiles/r02_notes.md) — SIMT divergence on cache-resident "
+                        "data, not DRAM.  Of the rooflines bench.py can measure live the FP32 one is the closest: credited flops per "
+                        "SURVEY Appendix C (30 / AABB test, 30 / sphere, 57 / quad, 42 / instance entry) of the work done by ACTIVE "
+                        "lanes (device counters); 0 for the flat extend kernel, which has no counters"}
     ach_hbm = ps["rays"] * EXTEND_BYTES_PER_RAY / (trav_ms * 1e-3) * 1e-9 if trav_ms > 0 else 0.0
     roofline_hbm = {"kernel": kernel_name, "bound": "hbm", "achieved": ach_hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach_hbm / peaks["hbm_gbs"], "peak_source": peak_src, "algorithmic_bytes_per_ray": EXTEND_BYTES_PER_RAY,
@@ -508,7 +513,7 @@ def run_ours(args):
         "config": {"workload": f"{scene_label} {W}x{H}, max_depth {args.max_depth}, {S} spp per step per GPU",
                    "spp_per_step_per_gpu": S, "paths_per_s": paths_all / (ms_all * 1e-3), "rays_per_path": rays_all / max(paths_all, 1),
                    "intersection_math": "fast (FMA)" if args.fast_math else "exact (bit-identical with the reference)",
-                   "flags": flags, "instance_split": st1["instance_split"],
+                   "flags": flags, "instance_mode": st1["instance_mode"],
                    "l2": "wavefront state per step (%.0f MB) exceeds L2; no explicit flush" % (W * H * S * 184 / 1e6),
                    "parallelism": f"sample-partition x{world}" if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "roofline": roofline, "roofline_hbm": roofline_hbm,
