@@ -225,6 +225,36 @@ def test_cpp_adapter_example(native_lib, tmp_path):
     assert data[:8] == b"\x89PNG\r\n\x1a\n" and len(data) > 10000
 
 
+def test_progressive_view_example(native_lib, tmp_path):
+    """examples/progressive_view.cpp = the LIVE branch of App::Run (App.cpp:176-242) without a window: one Update per loop
+    iteration, an RGBA8 Pixels() preview every K iterations, and scripted UI events — the "Reset" button (RayTracer.cpp:79-85), a
+    window resize (RayTracer.cpp:72-77 -> OnResize) and "Load Scene" (App.cpp:220-227: a failed load keeps the scene)."""
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "progressive_view"
+    lib_dir = os.path.join(ROOT, "raytrace2_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "progressive_view.cpp"),
+                           "-L" + lib_dir, "-lraytrace2_b200", "-Wl,-rpath," + lib_dir, "-o", str(exe)])
+    prefix = str(tmp_path / "pv")
+    out = subprocess.run([str(exe), scene_path("cornell_original_test"), prefix, "40", "8", "12:reset", "20:resize:120x80",
+                          "26:load:" + scene_path("does_not_exist"), "30:load:" + scene_path("cornell_box4")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    log = out.stdout
+    # frame counter: +1 per Update; Reset / OnResize / Load Scene restart it (RayTracer.cpp:49-53,87-104; App.cpp:224-226)
+    assert "[7] Frame Count 8 " in log and "[12] Reset -> Frame Count 0" in log and "[15] Frame Count 4 " in log
+    assert "[20] OnResize 120x80 -> Frame Count 0" in log and "[23] Frame Count 4 " in log and "(120x80)" in log
+    assert "[26] Load Scene" in log and "failed" in log and "(scene kept)" in log
+    assert "[30] Load Scene" in log and "[31] Frame Count 2 " in log and "[39] Frame Count 10 " in log
+    # previews: binary PPMs of the current dims, not black, getting smoother (fewer distinct noisy values is hard to assert; check size + content)
+    first = open(prefix + "_0.ppm", "rb").read()
+    assert first.startswith(b"P6\n600 600\n255\n") and len(first) == len(b"P6\n600 600\n255\n") + 600 * 600 * 3
+    px = np.frombuffer(first[len(b"P6\n600 600\n255\n"):], np.uint8)
+    assert px.mean() > 5
+    small = open(prefix + "_2.ppm", "rb").read()
+    assert small.startswith(b"P6\n120 80\n255\n")
+
+
 def test_cli_binary(native_lib, tmp_path):
     """raytrace2_b200/bin/raytrace_2 <scene-without-.json> <out.png> with $RAYTRACE2_ROOT/local/data/settings.json."""
     import subprocess
