@@ -284,7 +284,7 @@ def time_config(rt, torch, D, args, name, dims, spp_step, steps=2, warmup=1):
     row = {"workload": f"{label} {W}x{H}, {spp_step} spp per step per GPU", "Mrays_per_s": rays / (ms_all * 1e-3) * 1e-6,
            "paths_per_s": paths / (ms_all * 1e-3), "rays_per_path": rays / max(paths, 1), "ms_per_step": ms_all / steps,
            "bvh_build_ms": st1["gpu_ms_bvh_build"], "instance_mode": st1["instance_mode"], "max_stack_need": st1["max_stack_need"],
-           "stack_overflows": st1["stack_overflows"]}
+           "compact_nodes": st1["compact_nodes"], "node_inflation": round(st1["node_inflation"], 4), "stack_overflows": st1["stack_overflows"]}
     del tracer, scene
     return row
 
@@ -514,6 +514,7 @@ def run_ours(args):
                    "spp_per_step_per_gpu": S, "paths_per_s": paths_all / (ms_all * 1e-3), "rays_per_path": rays_all / max(paths_all, 1),
                    "intersection_math": "fast (FMA)" if args.fast_math else "exact (bit-identical with the reference)",
                    "flags": flags, "instance_mode": st1["instance_mode"],
+                   "compact_nodes": st1["compact_nodes"], "node_inflation": round(st1["node_inflation"], 4),
                    "l2": "wavefront state per step (%.0f MB) exceeds L2; no explicit flush" % (W * H * S * 184 / 1e6),
                    "parallelism": f"sample-partition x{world}" if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "roofline": roofline, "roofline_hbm": roofline_hbm,

@@ -251,6 +251,8 @@ typedef struct rt2_renderer rt2_renderer;
 #define RT2_FLAG_LBVH_PLOC 512u /* with RT2_FLAG_GPU_LBVH: build the hierarchy by PLOC (parallel locally-ordered clustering over the
                                    Morton order) instead of Karras' one-pass radix tree.  Measured WORSE on the sphere stress scene
                                    (38.7 vs 30.0 node pairs per ray at 1 M spheres): opt-in, for A/B */
+#define RT2_FLAG_FLOAT_NODES 1024u /* keep the 64-byte float node pairs even where the 32-byte quantised pairs would be used (A/B;
+                                     same hits: box tests only cull) */
 #define RT2_FLAG_INSTANCE_SPLIT 256u /* two passes: surfaces-only world tree, then one {ray, instance} entry per touched instance
                                    (RT2_MAX_HOISTED_INSTANCES); measured equal to the inline walk, kept for A/B */
 
@@ -300,6 +302,8 @@ typedef struct rt2_stats {
   double gpu_ms_extend_inst; /* instance split, while profiling: time of the instance pass (gpu_ms_extend = the world pass) */
   uint32_t max_stack_need;  /* stack entries the deepest traversal of this scene can need (tree depths, verified <= 63 at upload) */
   uint32_t instance_mode;   /* 0 no instances, 1 inline TLAS -> BLAS, 2 two-pass split, 3 unified world tree, 4 flat extend */
+  uint32_t compact_nodes;   /* 1 iff the walk reads 32-byte node pairs with boxes quantised onto one 15-bit grid per scene */
+  float node_inflation;     /* mean over the node boxes of (quantised / float surface area) - 1: the measure the choice is made on */
 } rt2_stats;
 
 typedef struct rt2_hit {

@@ -29,6 +29,7 @@ RT2_FLAG_INSTANCES_INLINE = 64
 RT2_FLAG_NO_INSTANCE_SPLIT = 64
 RT2_FLAG_INSTANCE_SPLIT = 256
 RT2_FLAG_LBVH_PLOC = 512
+RT2_FLAG_FLOAT_NODES = 1024
 RT2_FLAG_NO_FLAT_EXTEND = 128
 RT2_MAX_HOISTED_INSTANCES = 4
 RT2_ABI_VERSION = 3
@@ -124,7 +125,8 @@ class Stats(C.Structure):
                 ("gpu_ms_other", C.c_double), ("gpu_ms_finish", C.c_double), ("gpu_ms_bvh_build", C.c_double), ("box_pair_tests", C.c_uint64),
                 ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("instance_visits", C.c_uint64), ("gpu_ms_sort", C.c_double),
                 ("stack_overflows", C.c_uint64), ("pending_frames", C.c_uint64), ("n_gpus", C.c_uint32), ("instance_split", C.c_uint32),
-                ("gpu_ms_extend_inst", C.c_double), ("max_stack_need", C.c_uint32), ("instance_mode", C.c_uint32)]
+                ("gpu_ms_extend_inst", C.c_double), ("max_stack_need", C.c_uint32), ("instance_mode", C.c_uint32),
+                ("compact_nodes", C.c_uint32), ("node_inflation", C.c_float)]
 
 
 class Hit(C.Structure):

@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "rt_lbvh.hpp"
+#include "rt_qnodes.hpp"
 #include "rt_render.hpp"
 #include "rt_shade.cuh"
 #ifdef RT2_WITH_RAY_SORT
@@ -154,7 +155,7 @@ __device__ __forceinline__ void flush_trav_counters(const TravCounters& cnt, boo
   if (cnt.overflow) atomicAdd(&totals[6], 1ull);  // never expected: the builders bound the tree depth
 }
 
-template <class M, bool kCount, int kMode>
+template <class M, bool kCount, int kMode, bool kQuant = false>
 __global__ void __launch_bounds__(kBlock, 4) k_traverse(const DeviceScene S, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
                                                         uint32_t* __restrict__ cursor, const float4* __restrict__ ray_o,
                                                         const float4* __restrict__ ray_d, float tmin, float tmax,
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse(const DeviceScene S, con
   // queues below the threshold were not sorted (rt_sort.cuh): consume them in queue order
   const uint32_t* ord = (order != nullptr && n >= sort_min_rays) ? order : nullptr;
   // scene.hittable_list.Hit(scene, r, Interval{0.001, kInfinity}, rec)  (RayTracer.cpp:25)
-  traverse_queue<M, kCount, kMode>(S, n, ray_o, ray_d, tmin, tmax, cursor, ord, trav, io, cnt, max_steps, fetch_threshold, s_ms);
+  traverse_queue<M, kCount, kMode, kQuant>(S, n, ray_o, ray_d, tmin, tmax, cursor, ord, trav, io, cnt, max_steps, fetch_threshold, s_ms);
   flush_trav_counters(cnt, kCount, totals);
 }
 
@@ -630,6 +631,9 @@ struct Renderer::Impl {
   void* d_inst_bounds{nullptr};
   size_t cap_flat_refs{0}, cap_flat_offsets{0}, cap_inst_bounds{0};
   bool flat_mode{false};  // tiny scene: k_traverse_flat instead of the BVH walk
+  bool quant_nodes{false};  // the walk reads the 32-byte quantised node pairs (rt_qnodes.cu) instead of the 64-byte float pairs
+  void* d_qnodes{nullptr};
+  size_t cap_qnodes{0};
   bool unified_mode{false};  // instances flattened into ONE world-space tree (kTravUnified): the default when the scene carries it
   void* d_inst_leaves{nullptr};
   size_t cap_inst_leaves{0};
@@ -700,7 +704,7 @@ Renderer::~Renderer() {
   cudaSetDevice(cfg_.device);
   FreeState();
   Impl& m = *impl_;
-  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_inst_bounds, m.d_images, m.d_image_texels, m.d_nodes4, m.d_inst_leaves};
+  void* bufs[] = {m.d_spheres, m.d_quads, m.d_xforms, m.d_instances, m.d_media, m.d_materials, m.d_textures, m.d_perlin, m.d_prim_refs, m.d_nodes, m.d_media_bounds, m.d_flat_refs, m.d_flat_offsets, m.d_inst_bounds, m.d_images, m.d_image_texels, m.d_nodes4, m.d_inst_leaves, m.d_qnodes};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (m.totals) cudaFree(m.totals);
@@ -1133,6 +1137,49 @@ int Renderer::UploadScene(const HostScene& scene) {
       return RT2_ERR_UNSUPPORTED;
     }
   }
+  // 32-byte node pairs for the unified and the inline walk (rt_qnodes.cu): used when the measured growth of the boxes' surface
+  // area — the expected number of extra node visits — stays small.  Scenes whose leaves are tiny against the scene's extent
+  // (BASELINE config 5: 10 M spheres of radius 0.2 over kilometres) keep the float nodes.
+  m.quant_nodes = false;
+  d.qnodes = nullptr;
+  node_inflation_ = 0.0f;
+  if (!m.flat_mode && !m.wide_mode && !m.split_mode && !(cfg_.flags & RT2_FLAG_FLOAT_NODES) && n_node_pairs_ > 0 &&
+      TuneInt("RT2_QUANT_NODES", 1) != 0) {
+    std::vector<uint32_t> roots;
+    if (m.unified_mode) {
+      roots.push_back(d.tlas_unified_root);
+    } else {
+      roots.push_back(d.tlas_root);
+      std::vector<rt2_instance> inst(scene.instances.size());
+      if (!inst.empty()) {
+        // (the device copy: a device build lays the trees out itself)
+        RT2_CUDA(cudaStreamSynchronize(m.stream));
+        RT2_CUDA(cudaMemcpy(inst.data(), m.d_instances, inst.size() * sizeof(rt2_instance), cudaMemcpyDeviceToHost));
+      }
+      for (const rt2_instance& in : inst) roots.push_back(in.blas_root);
+    }
+    if (roots.size() <= 4096) {
+      const size_t bytes = static_cast<size_t>(n_node_pairs_) * 32;
+      if (bytes > m.cap_qnodes || m.d_qnodes == nullptr) {
+        if (m.d_qnodes) cudaFree(m.d_qnodes);
+        m.d_qnodes = nullptr;
+        m.cap_qnodes = 0;
+        RT2_CUDA(cudaMalloc(&m.d_qnodes, bytes));
+        m.cap_qnodes = bytes;
+      }
+      NodeGrid grid{};
+      rc = QuantiseNodesOnDevice(m.d_nodes, n_node_pairs_, roots.data(), static_cast<uint32_t>(roots.size()), m.d_qnodes, &grid, m.stream,
+                                 &launches_, &err_);
+      if (rc != RT2_OK) return rc;
+      node_inflation_ = static_cast<float>(grid.inflation);
+      const float limit = TuneFloat("RT2_QUANT_MAX_INFLATION", kQuantMaxInflation);
+      if (grid.usable && grid.inflation <= limit) {
+        m.quant_nodes = true;
+        d.qnodes = static_cast<const uint4*>(m.d_qnodes);
+        for (int k = 0; k < 3; k++) d.q_base[k] = grid.base[k], d.q_ext[k] = grid.ext[k];
+      }
+    }
+  }
   if (m.split_mode && (!was_split || !m.split.entries) && width_ > 0) {
     rc = AllocSplitState();  // a re-upload switched the renderer into split mode after Resize
     if (rc != RT2_OK) return rc;
@@ -1503,9 +1550,14 @@ static void LaunchExtendT(Renderer::Impl& m, const ExtendArgs& a, uint64_t* laun
     k_traverse_flat<M><<<a.grid_flat, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.ray_o, a.ray_d, a.tmin, a.tmax, a.trav);
     (*launches)++;
   } else if (m.unified_mode) {
-    k_traverse<M, kCount, kTravUnified><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
-                                                                            a.order, a.sort_min_rays, a.trav, SplitIO{}, m.totals,
-                                                                            m.trav_max_steps, m.trav_fetch_threshold);
+    if (m.quant_nodes)
+      k_traverse<M, kCount, kTravUnified, true><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin,
+                                                                                    a.tmax, a.order, a.sort_min_rays, a.trav, SplitIO{},
+                                                                                    m.totals, m.trav_max_steps, m.trav_fetch_threshold);
+    else
+      k_traverse<M, kCount, kTravUnified><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
+                                                                              a.order, a.sort_min_rays, a.trav, SplitIO{}, m.totals,
+                                                                              m.trav_max_steps, m.trav_fetch_threshold);
     (*launches)++;
   } else if (m.split_mode) {
     SplitIO io = a.io;
@@ -1520,9 +1572,14 @@ static void LaunchExtendT(Renderer::Impl& m, const ExtendArgs& a, uint64_t* laun
                                                                          m.trav_fetch_threshold);
     *launches += 2;
   } else {
-    k_traverse<M, kCount, kTravInline><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
-                                                                           a.order, a.sort_min_rays, a.trav, SplitIO{}, m.totals,
-                                                                           m.trav_max_steps, m.trav_fetch_threshold);
+    if (m.quant_nodes)
+      k_traverse<M, kCount, kTravInline, true><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin,
+                                                                                   a.tmax, a.order, a.sort_min_rays, a.trav, SplitIO{},
+                                                                                   m.totals, m.trav_max_steps, m.trav_fetch_threshold);
+    else
+      k_traverse<M, kCount, kTravInline><<<a.grid, kBlock, 0, m.stream>>>(m.ds, a.n_ptr, a.n_fixed, a.cursor, a.ray_o, a.ray_d, a.tmin, a.tmax,
+                                                                             a.order, a.sort_min_rays, a.trav, SplitIO{}, m.totals,
+                                                                             m.trav_max_steps, m.trav_fetch_threshold);
     (*launches)++;
   }
 }
@@ -2202,6 +2259,8 @@ int Renderer::GetStats(rt2_stats* out) {
   out->pending_frames = pending_frames_;
   out->n_gpus = 1;
   out->instance_split = m.split_mode ? 1u : 0u;
+  out->compact_nodes = m.quant_nodes ? 1u : 0u;
+  out->node_inflation = node_inflation_;
   out->instance_mode = m.flat_mode ? 4u : (m.unified_mode ? 3u : (m.split_mode ? 2u : (m.ds.n_instances ? 1u : 0u)));
   return RT2_OK;
 }

@@ -320,6 +320,8 @@ int MultiRenderer::GetStats(rt2_stats* out) {
     out->gpu_ms_bvh_build = std::max(out->gpu_ms_bvh_build, s.gpu_ms_bvh_build);
     out->instance_split = s.instance_split;
     out->instance_mode = s.instance_mode;
+    out->compact_nodes = s.compact_nodes;
+    out->node_inflation = s.node_inflation;
     out->max_stack_need = std::max(out->max_stack_need, s.max_stack_need);
   }
   out->frames = frames_;

@@ -85,6 +85,7 @@ class Renderer {
   uint32_t world_depth_{0};
   uint32_t n_textures_{0};
   std::vector<uint32_t> tree_depths_;  // node-pair depth of the trees on the device: [0] TLAS, [1 + i] BLAS of instance i, ...
+  float node_inflation_{0.0f};         // surface-area growth of the quantised node boxes (rt_qnodes.cu)
   uint32_t max_stack_need_{0};         // stack entries the deepest traversal of this scene can need (checked against kStackSize)
   uint64_t launches_{0};
   double gpu_ms_total_{0};

@@ -52,6 +52,11 @@ struct DeviceScene {
   uint32_t n_spheres, n_quads, n_materials, n_textures, n_node_pairs, n_prim_refs, n_inst_leaves;
   const uint32_t* __restrict__ prim_refs;
   const float4* __restrict__ nodes;  // 4 x float4 per node pair
+  // compact node pairs (rt_qnodes.cu), nullptr when the scene keeps the float nodes: 2 x uint4 per pair, 15-bit boxes on one grid
+  // per scene; a stored coordinate decodes to v in [1, 2) and means x = q_base + v * q_ext
+  const uint4* __restrict__ qnodes;
+  float q_base[3];
+  float q_ext[3];
   uint32_t tlas_root;        // world TLAS with the instances as singleton leaves (kTravInline)
   uint32_t tlas_world_root;  // world TLAS over surfaces only (kTravWorld: the instances are hoisted out of the tree)
   uint32_t tlas_unified_root;  // world tree over surfaces + every instanced primitive as a world-space leaf (kTravUnified)
@@ -81,6 +86,8 @@ __host__ __device__ inline uint32_t make_leaf_entry(uint32_t first, uint32_t cou
   return count == 1u ? (kLeafFlag | kLeafDirect | ref_if_single) : (kLeafFlag | ((count - 1u) << 26) | first);
 }
 constexpr int kStackSize = 64;
+// The 32-byte quantised node pairs are used when they grow the boxes' total surface area by at most this fraction.
+constexpr float kQuantMaxInflation = 0.05f;
 
 struct RaySpace {
   F3 o, d;
@@ -341,7 +348,7 @@ __device__ __forceinline__ uint4 load_closest(const DeviceScene& S, const uint4*
   return tr;
 }
 
-template <class M, bool kCount, int kMode>
+template <class M, bool kCount, int kMode, bool kQuant = false>
 __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n, const float4* __restrict__ ray_o,
                                                const float4* __restrict__ ray_d, float tmin, float tmax,
                                                uint32_t* __restrict__ next_ray, const uint32_t* __restrict__ order,
@@ -378,7 +385,13 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
     d = nd;
     a = vdot<M>(d, d);
     inv = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
-    oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
+    if (kQuant) {
+      // fold the node grid into the slab coefficients: t = (q_base + v * q_ext - o) / d = v * (q_ext / d) + (q_base - o) / d
+      oid = {(S.q_base[0] - o.x) * inv.x, (S.q_base[1] - o.y) * inv.y, (S.q_base[2] - o.z) * inv.z};
+      inv = {S.q_ext[0] * inv.x, S.q_ext[1] * inv.y, S.q_ext[2] * inv.z};
+    } else {
+      oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
+    }
   };
   // `top` mirrors the stack's top entry (slot sp - 1) in a register.  Every push / pop ends with an
   // unconditional reload of the new top, issued a whole node step before it can be needed, so a pop never waits for a load
@@ -490,9 +503,28 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
       for (int step = 0; step < max_steps && active && !(cur & kLeafFlag); step++) {
         RT2_CHECK(cur < S.n_node_pairs, kChkNode);
         RT2_CHECK(sp >= 2 && sp <= kStackSize, kChkStack);
-        const float4* np = S.nodes + static_cast<size_t>(cur) * 4;
-        // (one 256-bit load per node — LDG.E.256 on sm_100 — measured 4 % SLOWER than these four 128-bit loads; r02 notes)
-        const float4 a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
+        // the two child boxes as {min, max} corners + traversal entries
+        float4 a0, a1, b0, b1;
+        uint32_t e0, e1;
+        if (kQuant) {
+          // 32-byte pair: 16-bit fields with the top bit set; PRMT {00, lo, hi, 3F} makes the float 1 + q / 32768 (rt_qnodes.cu)
+          const uint4* np = S.qnodes + static_cast<size_t>(cur) * 2;
+          const uint4 qa = __ldg(np + 0), qb = __ldg(np + 1);
+          auto lo16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7104u)); };
+          auto hi16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7324u)); };
+          a0 = make_float4(lo16(qa.x), hi16(qa.x), lo16(qa.y), 0.0f);
+          a1 = make_float4(hi16(qa.y), lo16(qa.z), hi16(qa.z), 0.0f);
+          b0 = make_float4(lo16(qb.x), hi16(qb.x), lo16(qb.y), 0.0f);
+          b1 = make_float4(hi16(qb.y), lo16(qb.z), hi16(qb.z), 0.0f);
+          e0 = qa.w, e1 = qb.w;
+        } else {
+          const float4* np = S.nodes + static_cast<size_t>(cur) * 4;
+          // (one 256-bit load per node — LDG.E.256 on sm_100 — measured 4 % SLOWER than these four 128-bit loads; r02 notes)
+          a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
+          // device node format (rt_kernels.cu UploadScene / rt_lbvh.cu): .w of the min corner is the traversal entry itself
+          // (interior -> child pair index; leaf -> see make_leaf_entry)
+          e0 = __float_as_uint(a0.w), e1 = __float_as_uint(b0.w);
+        }
         if (kCount) cnt.box_pairs++;
         // conservative culling: near is shrunk by 1e-6 relative before it is compared with far and with the (scaled)
         // closest hit so far; an empty slot has NaN bounds -> far is NaN -> never entered
@@ -511,9 +543,6 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         const float far1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
         const float n1 = near1 * 0.999999f;
         const bool h1 = (n1 <= far1) && (n1 <= bound);
-        // device node format (rt_kernels.cu UploadScene / rt_lbvh.cu): .w of the min corner is the traversal entry itself:
-        // (interior -> child pair index; leaf -> see make_leaf_entry)
-        const uint32_t e0 = __float_as_uint(a0.w), e1 = __float_as_uint(b0.w);
         // branch-free step: the far child of a double hit is stored above the top (a harmless write when it is not pushed),
         // a miss takes the register copy of the top
         const bool both = h0 && h1, any = h0 || h1;
@@ -521,7 +550,8 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
         const uint32_t near_child = (h0 && !swap) ? e0 : e1;
         const uint32_t far_child = swap ? e0 : e1;
         st_store(sp, far_child);
-        // (prefetching the far child's node pair into L1 here, for the later pop: measured 5 931 vs 6 030 Mrays/s — dropped)
+        // (prefetching the far child's node pair into L1 here, for the later pop: measured 5 931 vs 6 030 Mrays/s — dropped;
+        //  predicating the store on `both` and the reload on a pop, so that only those lanes touch L1: 6 086 vs 6 182 — dropped)
         if (kMode == kTravInline) {
           if (any) {
             cur = near_child;
@@ -538,84 +568,83 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
       }
       __syncwarp();
       // phase 2: leaves
-      if (active && (cur & kLeafFlag) && cur != kTravDone) {
-        const bool direct = (cur & kLeafDirect) != 0u;
-        const uint32_t first = cur & 0x03FFFFFFu;
-        const uint32_t count = direct ? 1u : (((cur >> 26) & 0xFu) + 1u);
+      // (Aila & Laine's postponed leaf — park a leaf met as the near child and keep walking, test it in the warp's next leaf
+      //  phase — measured 6 087 vs 6 184 Mrays/s on book 2: 5 % more node visits for culling against a stale closest hit)
+      const uint32_t leaf = cur;
+      if (active && (leaf & kLeafFlag) && leaf != kTravDone) {
+        const bool direct = (leaf & kLeafDirect) != 0u;
+        const uint32_t first = leaf & 0x03FFFFFFu;
+        const uint32_t count = direct ? 1u : (((leaf >> 26) & 0xFu) + 1u);
         bool entered = false;
         for (uint32_t i = 0; i < count; i++) {
           RT2_CHECK(direct || first + i < S.n_prim_refs, kChkPrimRef);
-          const uint32_t ref = direct ? (cur & 0x3FFFFFFFu) : __ldg(S.prim_refs + first + i);
+          const uint32_t ref = direct ? (leaf & 0x3FFFFFFFu) : __ldg(S.prim_refs + first + i);
           const uint32_t type = RT2_PRIM_TYPE(ref), idx = RT2_PRIM_INDEX(ref);
           RT2_CHECK(type != RT2_PRIM_SPHERE || idx < S.n_spheres, kChkSphere);
           RT2_CHECK(type != RT2_PRIM_QUAD || idx < S.n_quads, kChkQuad);
           RT2_CHECK(type != RT2_PRIM_INSTANCE || kMode != kTravUnified || idx < S.n_inst_leaves, kChkInstLeaf);
           RT2_CHECK(type != RT2_PRIM_INSTANCE || kMode != kTravInline || idx < S.n_instances, kChkInstance);
           RT2_CHECK(type <= RT2_PRIM_INSTANCE && (type != RT2_PRIM_INSTANCE || kMode == kTravUnified || kMode == kTravInline), kChkPrimRef);
-          if (type == RT2_PRIM_SPHERE) {
-            if (kCount) cnt.spheres++;
-            float t;
-            if (sphere_hit<M>(__ldg(S.spheres + 2 * idx), __ldg(S.spheres + 2 * idx + 1), o, d, a, time, tmin, best.t, t)) {
-              best.t = t;
-              best.prim = ref;
-              best.instance = (kMode == kTravUnified) ? -1 : cur_inst;  // kTravUnified: cur_inst is the cached instance
-            }
-          } else if (type == RT2_PRIM_QUAD) {
-            if (kCount) cnt.quads++;
-            float t;
-            if (quad_hit<M>(S.quads + 5 * idx, o, d, tmin, best.t, t) && quad_wins_tie(S, t, ref, best)) {
-              best.t = t;
-              best.prim = ref;
-              best.instance = (kMode == kTravUnified) ? -1 : cur_inst;
-            }
-          } else if (kMode == kTravUnified) {
-            // instanced leaf: primitive il.x of instance il.y, tested in the instance's model space (Transform.cpp:13-20,75-88)
-            const uint2 il = __ldg(S.inst_leaves + idx);
-            RT2_CHECK(il.y < S.n_instances, kChkInstance);
-            RT2_CHECK(RT2_PRIM_TYPE(il.x) == RT2_PRIM_SPHERE ? RT2_PRIM_INDEX(il.x) < S.n_spheres : RT2_PRIM_INDEX(il.x) < S.n_quads, kChkInstLeaf);
-            float* ms = ms_cache + threadIdx.x;
-            if (cur_inst != static_cast<int32_t>(il.y)) {
+          // The primitive and the ray it is tested with: a world leaf takes the world ray, an instanced leaf (kTravUnified) its
+          // instance's model-space ray — then ONE sphere / quad test serves both, so the lanes of a warp split by primitive
+          // type only, not by (type, space).
+          uint32_t pref = ref;
+          int32_t pinst = (kMode == kTravUnified) ? -1 : cur_inst;  // kTravUnified: cur_inst is the cached instance
+          F3 ro = o, rd = d;
+          float ra = a;
+          if (type == RT2_PRIM_INSTANCE) {
+            if (kMode == kTravUnified) {
+              // instanced leaf: primitive il.x of instance il.y, tested in the instance's model space (Transform.cpp:13-20,75-88)
+              const uint2 il = __ldg(S.inst_leaves + idx);
+              RT2_CHECK(il.y < S.n_instances, kChkInstance);
+              RT2_CHECK(RT2_PRIM_TYPE(il.x) == RT2_PRIM_SPHERE ? RT2_PRIM_INDEX(il.x) < S.n_spheres : RT2_PRIM_INDEX(il.x) < S.n_quads, kChkInstLeaf);
+              float* ms = ms_cache + threadIdx.x;
+              if (cur_inst != static_cast<int32_t>(il.y)) {
+                if (kCount) cnt.instances++;
+                const uint4 in = __ldg(S.instances + il.y);
+                const RaySpace r = to_chain_space<M>(S, in.x, in.y, RaySpace{o, d});
+                ms[0 * blockDim.x] = r.o.x, ms[1 * blockDim.x] = r.o.y, ms[2 * blockDim.x] = r.o.z;
+                ms[3 * blockDim.x] = r.d.x, ms[4 * blockDim.x] = r.d.y, ms[5 * blockDim.x] = r.d.z;
+                ms[6 * blockDim.x] = vdot<M>(r.d, r.d);
+                cur_inst = static_cast<int32_t>(il.y);
+              }
+              ro = {ms[0 * blockDim.x], ms[1 * blockDim.x], ms[2 * blockDim.x]};
+              rd = {ms[3 * blockDim.x], ms[4 * blockDim.x], ms[5 * blockDim.x]};
+              ra = ms[6 * blockDim.x];
+              pref = il.x;
+              pinst = static_cast<int32_t>(il.y);
+            } else if (kMode == kTravInline) {
+              // instance leaf (always a singleton leaf of the TLAS, host/bvh_build.cpp): enter its BLAS in model space
               if (kCount) cnt.instances++;
-              const uint4 in = __ldg(S.instances + il.y);
-              const RaySpace r = to_chain_space<M>(S, in.x, in.y, RaySpace{o, d});
-              ms[0 * blockDim.x] = r.o.x, ms[1 * blockDim.x] = r.o.y, ms[2 * blockDim.x] = r.o.z;
-              ms[3 * blockDim.x] = r.d.x, ms[4 * blockDim.x] = r.d.y, ms[5 * blockDim.x] = r.d.z;
-              ms[6 * blockDim.x] = vdot<M>(r.d, r.d);
-              cur_inst = static_cast<int32_t>(il.y);
+              const uint4 in = __ldg(S.instances + idx);
+              const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
+              RaySpace ms = to_chain_space<M>(S, in.x, in.y, RaySpace{make_f3(wo), make_f3(wd)});
+              set_space(ms.o, ms.d);
+              cur_inst = static_cast<int32_t>(idx);
+              cur_cull = 1.0f;
+              st_store(sp++, kStackSentinel);
+              top = kStackSentinel;
+              cur = in.z;
+              entered = true;
+              break;
             }
-            const F3 mo = {ms[0 * blockDim.x], ms[1 * blockDim.x], ms[2 * blockDim.x]};
-            const F3 md = {ms[3 * blockDim.x], ms[4 * blockDim.x], ms[5 * blockDim.x]};
-            const uint32_t pidx = RT2_PRIM_INDEX(il.x);
-            float t;
-            if (RT2_PRIM_TYPE(il.x) == RT2_PRIM_SPHERE) {
-              if (kCount) cnt.spheres++;
-              if (sphere_hit<M>(__ldg(S.spheres + 2 * pidx), __ldg(S.spheres + 2 * pidx + 1), mo, md, ms[6 * blockDim.x], time, tmin, best.t, t)) {
-                best.t = t;
-                best.prim = il.x;
-                best.instance = static_cast<int32_t>(il.y);
-              }
-            } else {
-              if (kCount) cnt.quads++;
-              if (quad_hit<M>(S.quads + 5 * pidx, mo, md, tmin, best.t, t) && quad_wins_tie(S, t, il.x, best)) {
-                best.t = t;
-                best.prim = il.x;
-                best.instance = static_cast<int32_t>(il.y);
-              }
+          }
+          const uint32_t pidx = RT2_PRIM_INDEX(pref);
+          float t;
+          if (RT2_PRIM_TYPE(pref) == RT2_PRIM_SPHERE) {
+            if (kCount) cnt.spheres++;
+            if (sphere_hit<M>(__ldg(S.spheres + 2 * pidx), __ldg(S.spheres + 2 * pidx + 1), ro, rd, ra, time, tmin, best.t, t)) {
+              best.t = t;
+              best.prim = pref;
+              best.instance = pinst;
             }
-          } else if (kMode == kTravInline) {
-            // instance leaf (always a singleton leaf of the TLAS, host/bvh_build.cpp): enter its BLAS in model space
-            if (kCount) cnt.instances++;
-            const uint4 in = __ldg(S.instances + idx);
-            const float4 wo = ray_o[ray_idx], wd = ray_d[ray_idx];
-            RaySpace ms = to_chain_space<M>(S, in.x, in.y, RaySpace{make_f3(wo), make_f3(wd)});
-            set_space(ms.o, ms.d);
-            cur_inst = static_cast<int32_t>(idx);
-            cur_cull = 1.0f;
-            st_store(sp++, kStackSentinel);
-            top = kStackSentinel;
-            cur = in.z;
-            entered = true;
-            break;
+          } else {
+            if (kCount) cnt.quads++;
+            if (quad_hit<M>(S.quads + 5 * pidx, ro, rd, tmin, best.t, t) && quad_wins_tie(S, t, pref, best)) {
+              best.t = t;
+              best.prim = pref;
+              best.instance = pinst;
+            }
           }
         }
         if (!entered) pop();
