@@ -51,7 +51,8 @@ TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_extend_traffic.json")
 # arithmetic credited per unit of algorithmic work: AABB slab test 30, sphere test 30 (to the
 # discriminant; a lower bound), quad test 57, instance visit 42
 FLOP_AABB, FLOP_SPHERE, FLOP_QUAD, FLOP_INSTANCE = 30, 30, 57, 42
-# scene-fetch bytes per unit of traversal work: one 64-byte node pair, 32 B per sphere, 80 B per quad
+# scene-fetch bytes per unit of traversal work: one 64-byte node pair (32 B when the scene uses the quantised
+# pairs, rt2_stats.compact_nodes), 32 B per sphere, 80 B per quad
 NODE_PAIR_BYTES, SPHERE_BYTES, QUAD_BYTES = 64, 32, 80
 
 
@@ -390,6 +391,10 @@ def run_ours(args):
         kernel_name = "k_traverse<kTravUnified>"
     else:
         kernel_name = "k_traverse<kTravInline>"
+    compact = bool(ps.get("compact_nodes", 0))
+    if compact and kernel_name.startswith("k_traverse<"):
+        kernel_name = kernel_name[:-1] + ", kQuant>"
+    node_pair_bytes = 32 if compact else NODE_PAIR_BYTES
     trav_ms = ext_ms + inst_ms  # both passes of the extend stage
     fp32_peak, l2_peak = C.c_double(0.0), C.c_double(0.0)
     lib.rt2_measure_fp32_peak(local_rank, C.byref(fp32_peak))
@@ -414,9 +419,9 @@ def run_ours(args):
                 "flop_per_ray": flops / max(ps["rays"], 1), "per_ray": per_ray,
                 "avg_launch_ms": trav_ms / n_trav_launches, "rays_per_launch": rays_per_launch,
                 "share_of_step": trav_ms / prof_total if prof_total > 0 else None,
-                "note": "the extend stage runs out of L1: ncu shows l1tex throughput at 88 % of peak, 58-65 % of issue slots busy at 13-17 of "
-                        "32 lanes and long-scoreboard as the top stall (profiles/r02_notes.md) — SIMT divergence on cache-resident "
-                        "data, not DRAM.  Of the rooflines bench.py can measure live the FP32 one is the closest: credited flops per "
+                "note": "the extend stage runs out of L1: ncu shows l1tex throughput at 88 % of peak (float nodes), 58-65 % of issue slots busy "
+                        "at 13-17 of 32 lanes and long-scoreboard as the top stall (profiles/r02_notes.md) — SIMT divergence on "
+                        "cache-resident data, not DRAM.  Of the rooflines bench.py can measure live the FP32 one is the closest: credited flops per "
                         "SURVEY Appendix C (30 / AABB test, 30 / sphere, 57 / quad, 42 / instance entry) of the work done by ACTIVE "
                         "lanes (device counters); 0 for the flat extend kernel, which has no counters"}
     ach_hbm = ps["rays"] * EXTEND_BYTES_PER_RAY / (trav_ms * 1e-3) * 1e-9 if trav_ms > 0 else 0.0
@@ -424,13 +429,14 @@ def run_ours(args):
                     "frac": ach_hbm / peaks["hbm_gbs"], "peak_source": peak_src, "algorithmic_bytes_per_ray": EXTEND_BYTES_PER_RAY,
                     "algorithmic_bytes_per_launch": EXTEND_BYTES_PER_RAY * rays_per_launch,
                     "note": "not the bound: the ray queues stream once, the scene is cache resident"}
-    fetch_bytes = ps["box_pair_tests"] * NODE_PAIR_BYTES + ps["sphere_tests"] * SPHERE_BYTES + ps["quad_tests"] * QUAD_BYTES
+    fetch_bytes = ps["box_pair_tests"] * node_pair_bytes + ps["sphere_tests"] * SPHERE_BYTES + ps["quad_tests"] * QUAD_BYTES
     ach_l2 = fetch_bytes / (trav_ms * 1e-3) * 1e-9 if trav_ms > 0 else 0.0
     roofline_l2 = {"kernel": kernel_name, "bound": "l2", "achieved": ach_l2, "peak": l2_peak.value, "unit": "GB/s",
                    "frac": ach_l2 / l2_peak.value if l2_peak.value > 0 else None,
                    "peak_source": "measured here (rt2_measure_l2_bandwidth: 24 MiB working set re-read with 16-byte loads)",
                    "scene_fetch_bytes_per_ray": fetch_bytes / max(ps["rays"], 1),
-                   "note": "scene fetches issued by active lanes (64 B per node pair, 32 B per sphere, 80 B per quad) — an upper bound of "
+                   "node_pair_bytes": node_pair_bytes,
+                   "note": "scene fetches issued by active lanes (64 B per float node pair / 32 B per quantised pair, 32 B per sphere, 80 B per quad) — an upper bound of "
                            "the L2 traffic: most of them hit L1 for scenes of a few hundred KB"}
     kernel_split = {"extend_world_ms": ext_ms, "extend_instances_ms": inst_ms, "finish_shade_ms": ps["gpu_ms_finish"],
                     "deferred_shade_ms": ps["gpu_ms_shade"], "sort_ms": ps["gpu_ms_sort"], "other_ms": ps["gpu_ms_other"], "steps": prof_steps}

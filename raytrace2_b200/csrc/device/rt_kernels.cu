@@ -155,8 +155,11 @@ __device__ __forceinline__ void flush_trav_counters(const TravCounters& cnt, boo
   if (cnt.overflow) atomicAdd(&totals[6], 1ull);  // never expected: the builders bound the tree depth
 }
 
+#ifndef RT2_TRAV_MIN_BLOCKS
+#define RT2_TRAV_MIN_BLOCKS 4  // 64 registers; 3 (85 registers, no spills, 24 warps per SM) measured slower — profiles/r02_notes.md
+#endif
 template <class M, bool kCount, int kMode, bool kQuant = false>
-__global__ void __launch_bounds__(kBlock, 4) k_traverse(const DeviceScene S, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
+__global__ void __launch_bounds__(kBlock, RT2_TRAV_MIN_BLOCKS) k_traverse(const DeviceScene S, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
                                                         uint32_t* __restrict__ cursor, const float4* __restrict__ ray_o,
                                                         const float4* __restrict__ ray_d, float tmin, float tmax,
                                                         const uint32_t* __restrict__ order, uint32_t sort_min_rays, uint4* trav,
@@ -685,7 +688,7 @@ struct Renderer::Impl {
   uint32_t* sort_bin_base{nullptr};
   int grid_sort{0};
   bool simple_media{false};  // every medium: one-primitive boundary, no instance chain (k_finish_shade<.., kMedia = 1>)
-  int trav_max_steps{8};  // node steps per round of the while-while traversal (measured: +12 % on the 1M-sphere scene, +1 % on book 2)
+  int trav_max_steps{8};  // node steps per round of the while-while traversal; set per scene in UploadScene
   int trav_fetch_threshold{kFetchThreshold};
   bool fused{true};               // k_finish_shade instead of k_finish_hit + per-bin shade kernels
   bool deferred_present[kNumBins]{};  // fused mode: bins that can receive noise-textured (deferred) materials
@@ -767,8 +770,6 @@ int Renderer::Init(const HostScene& scene, const rt2_config& cfg) {
   if (cfg_.frame_stride < 1) cfg_.frame_stride = 1;
   // persistent grids: resident blocks per SM x SM count
   int occ = 0;
-  m.trav_max_steps = static_cast<int>(TuneInt("RT2_TRAV_STEPS", m.trav_max_steps));
-  m.trav_fetch_threshold = static_cast<int>(TuneInt("RT2_TRAV_FETCH", m.trav_fetch_threshold));
   if (cfg_.flags & RT2_FLAG_FAST_MATH) {
     RT2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<FastMath, false, kTravInline>, kBlock, 0));
   } else {
@@ -1120,6 +1121,12 @@ int Renderer::UploadScene(const HostScene& scene) {
     d.inst_leaves = static_cast<const uint2*>(m.d_inst_leaves);
     d.tlas_unified_root = unified_root_;
   }
+  // Round length (node steps before the warp's leaf phase) and refill threshold (busy lanes below which the warp fetches new rays)
+  // of the while-while walk.  Measured optima (profiles/r02_notes.md): the unified walk, whose leaf phase serves world and
+  // instanced primitives with one test, wants shorter rounds — 6 / 24: book 2 6 572 Mrays/s against 6 300 at 8 / 20; the plain walk
+  // keeps 8 / 20 (book 1 10 032 against 9 978, 1 M spheres 2 901 against 2 780).
+  m.trav_max_steps = static_cast<int>(TuneInt("RT2_TRAV_STEPS", m.unified_mode ? 6 : 8));
+  m.trav_fetch_threshold = static_cast<int>(TuneInt("RT2_TRAV_FETCH", m.unified_mode ? 24 : kFetchThreshold));
   d.n_hoisted = m.split_mode ? static_cast<uint32_t>(scene.instances.size()) : 0u;
   d.tlas_world_root = m.split_mode ? world_root_ : d.tlas_root;
   {

@@ -6,7 +6,7 @@ tag=$1; shift
 envs=()
 while [ $# -gt 0 ] && [ "$1" != "--" ]; do envs+=("$1"); shift; done
 [ "$1" == "--" ] && shift
-env "${envs[@]}" timeout 600 python bench.py --no-configs --frame-spp 0 --no-cpu-baseline --steps 6 "$@" > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+env "${envs[@]}" timeout 120 python bench.py --no-configs --frame-spp 0 --no-cpu-baseline --steps 6 "$@" > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
 python - "$tag" <<'PY'
 import json, sys
 tag = sys.argv[1]
