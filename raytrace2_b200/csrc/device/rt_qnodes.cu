@@ -7,6 +7,8 @@
 // Boxes are rounded outwards and padded by one cell, so the quantised box contains the float box with a margin far above the
 // rounding error of the folded slab test: closest hits cannot change (box tests only cull).  Whether a scene
 // uses these nodes is decided from the measured surface-area inflation (Renderer::UploadScene).
+// The pairs keep the builder's (depth-first) order: laying the top 6 / 10 / 14 / all levels out breadth first, so that the nodes
+// every ray visits share cache lines, measured 6 557 / 6 560 / 6 550 / 6 549 against 6 545 Mrays/s — L1 capacity is not the limit.
 #include <cuda_runtime.h>
 
 #include <cmath>
