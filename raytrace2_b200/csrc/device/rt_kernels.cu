@@ -5,7 +5,9 @@
 //   k_generate            Camera::GetRay for F frames x W*H pixels                       (Camera.hpp:50-67)
 //   per bounce b < max_depth:
 //     [k_sort_*]          optional: coherence order of the queue                          (RT2_FLAG_SORT_RAYS, rt_sort.cuh)
-//     k_traverse          closest SURFACE: persistent while-while walk of TLAS -> instance BLAS (rt_trace.cuh);
+//     k_traverse          closest SURFACE: persistent while-while walk (rt_trace.cuh) of the unified world tree (scenes with
+//                         instances) or the TLAS -> instance BLAS pair, over 32-byte quantised node pairs where the scene's
+//                         leaves are large against the grid cell (rt_qnodes.cu), 64-byte float pairs otherwise;
 //       | k_traverse_flat   tiny scenes: every primitive, uniform loops, no tree
 //       | k_traverse_wide   RT2_FLAG_WIDE_BVH: 4-wide quantised nodes             (rt_wide.cuh)
 //     [k_media]           scenes whose media have list boundaries: media sampling as its own pass
@@ -16,7 +18,7 @@
 //   k_accumulate          accum[pixel] += radiance[f][pixel] in frame order                (RayTracer.cpp:64)
 //   k_resolve | k_resolve_peers   mean, RGBA8 preview; across GPUs over peer memory        (RayTracer.cpp:16-18,65-66,105-112)
 //
-// Queue sizes live in device memory (counters[bounce][8]); kernels are launched with a persistent grid and loop
+// Queue sizes live in device memory (counters[bounce][kCounterStride]); kernels are launched with a persistent grid and loop
 // grid-stride over the count they read there, so no host synchronisation happens inside a batch.
 #include <cuda_runtime.h>
 

@@ -299,6 +299,8 @@ struct TravCounters {
 // lanes instead of whichever lanes happen to reach a leaf in the same iteration.  When fewer than `fetch_threshold` lanes
 // are busy the warp pulls new work from the queue with one atomic.  `order` (optional) is the permutation in which the
 // queue is consumed.  Results go to trav_out[ray] = {t bits, prim ref, instance, has-entries flag}.
+// kQuant: the walk reads the 32-byte quantised node pairs (DeviceScene::qnodes, rt_qnodes.cu) instead of the float pairs;
+// the boxes are supersets of the float boxes, so the leaves reached — and the closest hit — are the same.
 enum { kTravInline = 0, kTravWorld = 1, kTravInst = 2, kTravUnified = 3 };
 constexpr uint32_t kFetchChunk = 64;  // queue items a warp reserves with one atomic (big queues)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
