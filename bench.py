@@ -204,8 +204,9 @@ def run_reference(args):
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic camera samples on the repo's scene file",
-        "config": {"workload": f"data/{args.scene}.json {wh[0]}x{wh[1]} max_depth {args.max_depth}, {spp} spp per step on the host CPU",
-                   "spp_per_step": spp, "paths_per_s": paths / total_sec},
+        # (the same `workload` string as the GPU arm prints: same scene file, size and depth; a step here is a bounded sample of it)
+        "config": {"workload": f"data/{args.scene}.json {wh[0]}x{wh[1]}, max_depth {args.max_depth}",
+                   "step": f"{spp} spp per step on the host CPU ({threads} threads)", "spp_per_step": spp, "paths_per_s": paths / total_sec},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind,
                          "sample": f"{args.steps} x {spp} spp at {wh[0]}x{wh[1]}, {total_sec:.1f} s of CPU work"},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -516,8 +517,8 @@ def run_ours(args):
         "metric": "Mrays/s", "value": rays_all / (ms_all * 1e-3) * 1e-6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic camera samples (Philox) on the repo's scene file; random Perlin tables",
-        "config": {"workload": f"{scene_label} {W}x{H}, max_depth {args.max_depth}, {S} spp per step per GPU",
-                   "spp_per_step_per_gpu": S, "paths_per_s": paths_all / (ms_all * 1e-3), "rays_per_path": rays_all / max(paths_all, 1),
+        "config": {"workload": f"{scene_label} {W}x{H}, max_depth {args.max_depth}",
+                   "step": f"{S} spp (one wavefront batch) per step per GPU", "spp_per_step_per_gpu": S, "paths_per_s": paths_all / (ms_all * 1e-3), "rays_per_path": rays_all / max(paths_all, 1),
                    "intersection_math": "fast (FMA)" if args.fast_math else "exact (bit-identical with the reference)",
                    "flags": flags, "instance_mode": st1["instance_mode"],
                    "compact_nodes": st1["compact_nodes"], "node_inflation": round(st1["node_inflation"], 4),
