@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kBlock, RT2_TRAV_MIN_BLOCKS) k_traverse(const 
                                                         int fetch_threshold) {
   const uint32_t n = n_ptr ? *n_ptr : n_fixed;
   TravCounters cnt;
-  __shared__ float s_ms[kMode == kTravUnified ? 7 * kBlock : 1];  // kTravUnified: model-space ray of the instance last met
+  __shared__ float s_ms[kMode == kTravUnified ? 14 * kBlock : 1];  // kTravUnified: world ray + model-space ray of the instance last met
   // queues below the threshold were not sorted (rt_sort.cuh): consume them in queue order
   const uint32_t* ord = (order != nullptr && n >= sort_min_rays) ? order : nullptr;
   // scene.hittable_list.Hit(scene, r, Interval{0.001, kInfinity}, rec)  (RayTracer.cpp:25)

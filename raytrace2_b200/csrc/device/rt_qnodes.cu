@@ -3,7 +3,9 @@
 // are stored as 15-bit coordinates on ONE grid per scene, each in a 16-bit field whose top bit is set: a single PRMT turns a
 // field into the float 1 + q / 32768 (bytes {00, lo, hi, 3F}), and the grid's origin and cell size are folded into the ray's
 // slab coefficients once per ray — the node step costs one PRMT per coordinate and no conversion instruction.
-//   pair = { uint4 child0, uint4 child1 },  child = { minx | miny << 16, minz | maxx << 16, maxy | maxz << 16, entry }
+//   pair = { uint4 child0, uint4 child1 },  child = { minx | maxx << 16, miny | maxy << 16, minz | maxz << 16, entry }
+// The min and max plane of an axis share a word, so a per-ray PRMT selector (low or high half, from the sign of the direction)
+// yields the plane the ray enters through or the one it leaves through directly: no min / max per axis in the slab test.
 // Boxes are rounded outwards and padded by one cell, so the quantised box contains the float box with a margin far above the
 // rounding error of the folded slab test: closest hits cannot change (box tests only cull).  Whether a scene
 // uses these nodes is decided from the measured surface-area inflation (Renderer::UploadScene).
@@ -74,8 +76,8 @@ __global__ void __launch_bounds__(kQBlock) k_quantise_nodes(const float4* __rest
         ratio_sum += static_cast<double>(half_area(eq[0], eq[1], eq[2]) / area);
       }
       const uint32_t kTop = 0x8000u;
-      qnodes[2ull * p + c] = make_uint4((kTop | qlo[0]) | ((kTop | qlo[1]) << 16), (kTop | qlo[2]) | ((kTop | qhi[0]) << 16),
-                                        (kTop | qhi[1]) | ((kTop | qhi[2]) << 16), __float_as_uint(mn[c].w));
+      qnodes[2ull * p + c] = make_uint4((kTop | qlo[0]) | ((kTop | qhi[0]) << 16), (kTop | qlo[1]) | ((kTop | qhi[1]) << 16),
+                                        (kTop | qlo[2]) | ((kTop | qhi[2]) << 16), __float_as_uint(mn[c].w));
     }
     if (!finite && (v0 || v1)) atomicAdd(&out[1], 1u);
   }

@@ -378,6 +378,8 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
   F3 o = {0, 0, 0}, d = {0, 0, 1};
   float time = 0.0f, a = 1.0f;
   F3 inv = {0, 0, 0}, oid = {0, 0, 0};
+  // kQuant: PRMT selectors of the NEAR and of the FAR plane's 16-bit field per axis
+  uint32_t sel_x = 0x7104u, sel_y = 0x7104u, sel_z = 0x7104u, fx = 0x7324u, fy = 0x7324u, fz = 0x7324u;
   float cull_scale = 1.0f, cur_cull = 1.0f;  // kTravInline
   int32_t cur_inst = -1;
   Closest best{tmax, RT2_PRIM_NONE, -1};
@@ -391,6 +393,10 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
       // fold the node grid into the slab coefficients: t = (q_base + v * q_ext - o) / d = v * (q_ext / d) + (q_base - o) / d
       oid = {(S.q_base[0] - o.x) * inv.x, (S.q_base[1] - o.y) * inv.y, (S.q_base[2] - o.z) * inv.z};
       inv = {S.q_ext[0] * inv.x, S.q_ext[1] * inv.y, S.q_ext[2] * inv.z};
+      // a ray enters a slab through the min plane (low half of the word) when it travels up the axis, else through the max plane
+      sel_x = inv.x < 0.0f ? 0x7324u : 0x7104u, fx = inv.x < 0.0f ? 0x7104u : 0x7324u;
+      sel_y = inv.y < 0.0f ? 0x7324u : 0x7104u, fy = inv.y < 0.0f ? 0x7104u : 0x7324u;
+      sel_z = inv.z < 0.0f ? 0x7324u : 0x7104u, fz = inv.z < 0.0f ? 0x7104u : 0x7324u;
     } else {
       oid = {-o.x * inv.x, -o.y * inv.y, -o.z * inv.z};
     }
@@ -476,6 +482,12 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
               const float4 wo = ray_o[idx], wd = ray_d[idx];
               time = wo.w;
               set_space(make_f3(wo), make_f3(wd));
+              if (kMode == kTravUnified) {
+                float* ws = ms_cache + threadIdx.x;
+                ws[0 * blockDim.x] = o.x, ws[1 * blockDim.x] = o.y, ws[2 * blockDim.x] = o.z;
+                ws[3 * blockDim.x] = d.x, ws[4 * blockDim.x] = d.y, ws[5 * blockDim.x] = d.z;
+                ws[6 * blockDim.x] = a;
+              }
               if (kMode == kTravInline || kMode == kTravUnified) {
                 // An instanced leaf reports t in model units (= world t * |M^-1 d|): a world-space box at parameter t_w can
                 // hold an instanced hit with raw t as small as t_w * sigma_min * |d|, so scale the TLAS culling bound.
@@ -507,44 +519,54 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
       for (int step = 0; step < max_steps && active && !(cur & kLeafFlag); step++) {
         RT2_CHECK(cur < S.n_node_pairs, kChkNode);
         RT2_CHECK(sp >= 2 && sp <= kStackSize, kChkStack);
-        // the two child boxes as {min, max} corners + traversal entries
-        float4 a0, a1, b0, b1;
+        // entry / exit parameters of the two child boxes + their traversal entries
         uint32_t e0, e1;
+        float near0, far0, near1, far1;
         if (kQuant) {
-          // 32-byte pair: 16-bit fields with the top bit set; PRMT {00, lo, hi, 3F} makes the float 1 + q / 32768 (rt_qnodes.cu)
+          // 32-byte pair, per child {minx | maxx << 16, miny | maxy << 16, minz | maxz << 16, entry}; every 16-bit field has its top
+          // bit set, so PRMT {00, lo, hi, 3F} IS the float 1 + q / 32768 (rt_qnodes.cu).  The per-ray selector picks the plane the
+          // ray ENTERS through (near) or leaves through (far) directly: t_near = min(t_min_plane, t_max_plane) needs no min / max.
           const uint4* np = S.qnodes + static_cast<size_t>(cur) * 2;
           const uint4 qa = __ldg(np + 0), qb = __ldg(np + 1);
-          auto lo16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7104u)); };
-          auto hi16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7324u)); };
-          a0 = make_float4(lo16(qa.x), hi16(qa.x), lo16(qa.y), 0.0f);
-          a1 = make_float4(hi16(qa.y), lo16(qa.z), hi16(qa.z), 0.0f);
-          b0 = make_float4(lo16(qb.x), hi16(qb.x), lo16(qb.y), 0.0f);
-          b1 = make_float4(hi16(qb.y), lo16(qb.z), hi16(qb.z), 0.0f);
+          // (prmt through inline PTX: __byte_perm() masks a run-time selector with 0x7777 first — one LOP3 per use)
+          auto dec = [](uint32_t w, uint32_t sel) {
+            uint32_t r;
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x3F000000u), "r"(sel));
+            return __uint_as_float(r);
+          };
+          if (kCount) cnt.box_pairs++;
+          near0 = fmaxf(fmaxf(fmaf(dec(qa.x, sel_x), inv.x, oid.x), fmaf(dec(qa.y, sel_y), inv.y, oid.y)),
+                        fmaxf(fmaf(dec(qa.z, sel_z), inv.z, oid.z), 0.0f));
+          far0 = fminf(fminf(fmaf(dec(qa.x, fx), inv.x, oid.x), fmaf(dec(qa.y, fy), inv.y, oid.y)), fmaf(dec(qa.z, fz), inv.z, oid.z));
+          near1 = fmaxf(fmaxf(fmaf(dec(qb.x, sel_x), inv.x, oid.x), fmaf(dec(qb.y, sel_y), inv.y, oid.y)),
+                        fmaxf(fmaf(dec(qb.z, sel_z), inv.z, oid.z), 0.0f));
+          far1 = fminf(fminf(fmaf(dec(qb.x, fx), inv.x, oid.x), fmaf(dec(qb.y, fy), inv.y, oid.y)), fmaf(dec(qb.z, fz), inv.z, oid.z));
           e0 = qa.w, e1 = qb.w;
         } else {
+          // 64-byte pair: {min, max} corners as floats
           const float4* np = S.nodes + static_cast<size_t>(cur) * 4;
           // (one 256-bit load per node — LDG.E.256 on sm_100 — measured 4 % SLOWER than these four 128-bit loads; r02 notes)
-          a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
+          const float4 a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
           // device node format (rt_kernels.cu UploadScene / rt_lbvh.cu): .w of the min corner is the traversal entry itself
           // (interior -> child pair index; leaf -> see make_leaf_entry)
           e0 = __float_as_uint(a0.w), e1 = __float_as_uint(b0.w);
+          if (kCount) cnt.box_pairs++;
+          float t0x = fmaf(a0.x, inv.x, oid.x), t1x = fmaf(a1.x, inv.x, oid.x);
+          float t0y = fmaf(a0.y, inv.y, oid.y), t1y = fmaf(a1.y, inv.y, oid.y);
+          float t0z = fmaf(a0.z, inv.z, oid.z), t1z = fmaf(a1.z, inv.z, oid.z);
+          near0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+          far0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+          t0x = fmaf(b0.x, inv.x, oid.x), t1x = fmaf(b1.x, inv.x, oid.x);
+          t0y = fmaf(b0.y, inv.y, oid.y), t1y = fmaf(b1.y, inv.y, oid.y);
+          t0z = fmaf(b0.z, inv.z, oid.z), t1z = fmaf(b1.z, inv.z, oid.z);
+          near1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+          far1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
         }
-        if (kCount) cnt.box_pairs++;
         // conservative culling: near is shrunk by 1e-6 relative before it is compared with far and with the (scaled)
         // closest hit so far; an empty slot has NaN bounds -> far is NaN -> never entered
         const float bound = (kMode == kTravInline) ? best.t * cur_cull : (kMode == kTravUnified ? best.t * cull_scale : best.t);
-        float t0x = fmaf(a0.x, inv.x, oid.x), t1x = fmaf(a1.x, inv.x, oid.x);
-        float t0y = fmaf(a0.y, inv.y, oid.y), t1y = fmaf(a1.y, inv.y, oid.y);
-        float t0z = fmaf(a0.z, inv.z, oid.z), t1z = fmaf(a1.z, inv.z, oid.z);
-        const float near0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-        const float far0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
         const float n0 = near0 * 0.999999f;
         const bool h0 = (n0 <= far0) && (n0 <= bound);
-        t0x = fmaf(b0.x, inv.x, oid.x), t1x = fmaf(b1.x, inv.x, oid.x);
-        t0y = fmaf(b0.y, inv.y, oid.y), t1y = fmaf(b1.y, inv.y, oid.y);
-        t0z = fmaf(b0.z, inv.z, oid.z), t1z = fmaf(b1.z, inv.z, oid.z);
-        const float near1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-        const float far1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
         const float n1 = near1 * 0.999999f;
         const bool h1 = (n1 <= far1) && (n1 <= bound);
         // branch-free step: the far child of a double hit is stored above the top (a harmless write when it is not pushed),
@@ -594,19 +616,29 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
           // type only, not by (type, space).
           uint32_t pref = ref;
           int32_t pinst = (kMode == kTravUnified) ? -1 : cur_inst;  // kTravUnified: cur_inst is the cached instance
-          F3 ro = o, rd = d;
-          float ra = a;
+          // kTravUnified: the world ray is parked in shared memory too (slots 0..6; the model-space ray in 7..13): it is needed by
+          // leaf tests only, and the node phase gets its seven registers
+          F3 ro, rd;
+          float ra;
+          if (kMode == kTravUnified) {
+            const float* ws = ms_cache + threadIdx.x;
+            ro = {ws[0 * blockDim.x], ws[1 * blockDim.x], ws[2 * blockDim.x]};
+            rd = {ws[3 * blockDim.x], ws[4 * blockDim.x], ws[5 * blockDim.x]};
+            ra = ws[6 * blockDim.x];
+          } else {
+            ro = o, rd = d, ra = a;
+          }
           if (type == RT2_PRIM_INSTANCE) {
             if (kMode == kTravUnified) {
               // instanced leaf: primitive il.x of instance il.y, tested in the instance's model space (Transform.cpp:13-20,75-88)
               const uint2 il = __ldg(S.inst_leaves + idx);
               RT2_CHECK(il.y < S.n_instances, kChkInstance);
               RT2_CHECK(RT2_PRIM_TYPE(il.x) == RT2_PRIM_SPHERE ? RT2_PRIM_INDEX(il.x) < S.n_spheres : RT2_PRIM_INDEX(il.x) < S.n_quads, kChkInstLeaf);
-              float* ms = ms_cache + threadIdx.x;
+              float* ms = ms_cache + threadIdx.x + 7 * blockDim.x;
               if (cur_inst != static_cast<int32_t>(il.y)) {
                 if (kCount) cnt.instances++;
                 const uint4 in = __ldg(S.instances + il.y);
-                const RaySpace r = to_chain_space<M>(S, in.x, in.y, RaySpace{o, d});
+                const RaySpace r = to_chain_space<M>(S, in.x, in.y, RaySpace{ro, rd});
                 ms[0 * blockDim.x] = r.o.x, ms[1 * blockDim.x] = r.o.y, ms[2 * blockDim.x] = r.o.z;
                 ms[3 * blockDim.x] = r.d.x, ms[4 * blockDim.x] = r.d.y, ms[5 * blockDim.x] = r.d.z;
                 ms[6 * blockDim.x] = vdot<M>(r.d, r.d);
