@@ -283,7 +283,7 @@ struct TravCounters {
 //   kTravUnified ONE world-space tree whose leaves are the world surfaces and, each with a conservative world-space box,
 //                every primitive of every instance (DeviceScene::inst_leaves).  An instanced leaf is still tested in its
 //                instance's model space with the reference's arithmetic (the model-space ray is computed once per ray and
-//                instance and parked in shared memory), so the leaves and their raw t are exactly those of the two-level
+//                instance and parked in shared memory, next to the world ray the other leaves are tested with), so the leaves and their raw t are exactly those of the two-level
 //                walks — but a ray bouncing inside an instance no longer walks the whole world tree first and the
 //                instance's tree second, and the closest hit found in either culls the other.
 //   kTravInst    pass 2: one lane = one entry.  The exact-arithmetic world-to-model transforms (Transform.cpp:13-20) run with
@@ -356,8 +356,8 @@ __device__ __forceinline__ void traverse_queue(const DeviceScene& S, uint32_t n,
                                                uint32_t* __restrict__ next_ray, const uint32_t* __restrict__ order,
                                                uint4* __restrict__ trav_out, const SplitIO& io, TravCounters& cnt,
                                                int max_steps, int fetch_threshold, float* __restrict__ ms_cache = nullptr) {
-  // ms_cache (kTravUnified): 7 x blockDim.x floats of shared memory — per thread the model-space ray (o, d, d.d) of the
-  // instance it last met
+  // ms_cache (kTravUnified): 14 x blockDim.x floats of shared memory — per thread the world ray (o, d, d.d) in slots 0..6 and the
+  // model-space ray of the instance it last met in slots 7..13
   const unsigned kFull = 0xFFFFFFFFu;
   const unsigned lane = threadIdx.x & 31u;
   // The traversal stack lives in local memory (L1-resident).  Slot 0 is never read as an entry (it absorbs the reload after
