@@ -283,9 +283,10 @@ struct TravCounters {
 //   kTravUnified ONE world-space tree whose leaves are the world surfaces and, each with a conservative world-space box,
 //                every primitive of every instance (DeviceScene::inst_leaves).  An instanced leaf is still tested in its
 //                instance's model space with the reference's arithmetic (the model-space ray is computed once per ray and
-//                instance and parked in shared memory, next to the world ray the other leaves are tested with), so the leaves and their raw t are exactly those of the two-level
-//                walks — but a ray bouncing inside an instance no longer walks the whole world tree first and the
-//                instance's tree second, and the closest hit found in either culls the other.
+//                instance and parked in shared memory, next to the world ray the other leaves are tested with), so the
+//                leaves and their raw t are exactly those of the two-level walks — but a ray bouncing inside an instance
+//                no longer walks the whole world tree first and the instance's tree second, and the closest hit found in
+//                either culls the other.
 //   kTravInst    pass 2: one lane = one entry.  The exact-arithmetic world-to-model transforms (Transform.cpp:13-20) run with
 //                the whole warp converged, the walk starts at the BLAS root with tmax = the ray's closest world surface,
 //                and a hit is merged into the ray's slot by a 64-bit atomicMin on (ordered t, entry index).
